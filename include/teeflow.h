@@ -1,0 +1,124 @@
+/*
+ * teeflow.h -- C ABI of libteeflow.so, the B200-native (sm_100a) TV-L1 dense optical-flow engine.
+ *
+ * Drop-in boundary for ONE path of nquach/TEE_optical_flow: the per-frame-pair TV-L1 call that the reference
+ * makes into OpenCV (file:line relative to /root/reference):
+ *
+ *   reference interface                                             replaced by
+ *   -------------------------------------------------------------   ---------------------------------------
+ *   cv2.optflow.createOptFlow_DualTVL1()                            teeflow_create
+ *        optical_flow/calculate_optical_flow.py:577
+ *   OF_model.setLambda(config.lambda_value)      (:578)             teeflow_set_param(h, "lambda", v)
+ *   OF_model.calc(saliency_1, saliency_2, None)  (:642)             teeflow_calc_pair_host
+ *   the serial pair loop of process_video        (:584-600)         teeflow_calc_clip / teeflow_calc_clip_host
+ *        (flow_list.append(flow_list[-1]); np.stack(..) * conversion_factor; .astype(float16) at :403)
+ *   cv2.cuda.OpticalFlowDual_TVL1 upload/calc/download (:633-639)   teeflow_calc_clip (device pointers)
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  All entry points return 0 on success or a negative
+ * teeflow_status; teeflow_last_error() gives the text.  A handle is bound to one CUDA device, owns its
+ * workspace, and is not thread-safe (use one handle per thread / per GPU).  There is no CPU fallback: without
+ * a CUDA device teeflow_create fails with TEEFLOW_ERR_CUDA.
+ */
+#ifndef TEEFLOW_H_
+#define TEEFLOW_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TEEFLOW_API __attribute__((visibility("default")))
+#else
+#define TEEFLOW_API
+#endif
+
+#define TEEFLOW_ABI_VERSION 1
+#define TEEFLOW_MAX_LEVELS 16
+
+typedef enum {
+    TEEFLOW_OK = 0,
+    TEEFLOW_ERR_BAD_ARG = -1,   /* NULL pointer, unknown key, value out of range */
+    TEEFLOW_ERR_BAD_SHAPE = -2, /* H/W/n_frames not supported or larger than the handle's capacity */
+    TEEFLOW_ERR_CUDA = -3,      /* a CUDA runtime call failed (text in teeflow_last_error) */
+    TEEFLOW_ERR_NCCL = -4,      /* reserved for the multi-GPU gather */
+    TEEFLOW_ERR_STATE = -5      /* internal scheduler did not converge (should never happen) */
+} teeflow_status;
+
+typedef enum { TEEFLOW_U8 = 0, TEEFLOW_F32 = 1 } teeflow_dtype;
+
+/* OpenCV DualTVL1OpticalFlow parameters (defaults of createOptFlow_DualTVL1).
+ * gamma and useInitialFlow are not exposed: the reference never sets them (gamma = 0, no initial flow). */
+typedef struct {
+    double tau;              /* 0.25 */
+    double lambda;           /* 0.15  == OpticalFlowCalculationConfig.lambda_value, config.py:177 */
+    double theta;            /* 0.3 */
+    double epsilon;          /* 0.01 */
+    double scale_step;       /* 0.8 */
+    int32_t nscales;         /* 5 */
+    int32_t warps;           /* 5 */
+    int32_t inner_iterations; /* 30 */
+    int32_t outer_iterations; /* 10 */
+    int32_t median_filtering; /* 5 (<=1 off, 3, 5) */
+    int32_t max_slots;       /* frame pairs solved concurrently (0 = default 64) */
+} teeflow_params;
+
+typedef struct teeflow_engine* teeflow_handle;
+
+TEEFLOW_API void teeflow_default_params(teeflow_params* p);
+TEEFLOW_API int teeflow_abi_version(void);
+
+TEEFLOW_API int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out);
+TEEFLOW_API int teeflow_destroy(teeflow_handle h);
+/* keys: tau lambda theta epsilon scale_step nscales warps inner_iterations outer_iterations median_filtering */
+TEEFLOW_API int teeflow_set_param(teeflow_handle h, const char* key, double value);
+TEEFLOW_API int teeflow_get_param(teeflow_handle h, const char* key, double* value);
+/* h may be NULL: returns the text of the last error raised without a handle (e.g. by teeflow_create) */
+TEEFLOW_API const char* teeflow_last_error(teeflow_handle h);
+
+/*
+ * Flow of every consecutive frame pair (i -> i+1) of one clip, all pairs in flight together.
+ *   frames_dev      device pointer, n_frames x H x W, dtype u8 (x1) or f32 in [0,1] (x255, like OpenCV)
+ *   frame_stride    elements between consecutive frames (>= H*W)
+ *   flow_f32_dev    device, [n_out, H, W, 2] float32, may be NULL;   n_out = n_frames-1 (+1 if duplicate_last)
+ *   flow_f16_dev    device, [n_out, H, W, 2] IEEE half (RNE),  may be NULL
+ *   out_scale       conversion_factor = pixel_spacing * frame_rate (calculate_optical_flow.py:538-541,600)
+ *   duplicate_last  append a copy of the last flow so that n_out == n_frames (:599)
+ *   stream          cudaStream_t (as void*) the caller's inputs are ready on; the call returns after the
+ *                   results are complete on that stream (it synchronises the stream).
+ */
+TEEFLOW_API int teeflow_calc_clip(teeflow_handle h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                      int64_t frame_stride, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
+                      int duplicate_last, void* stream);
+
+/* Generic form: n_pairs arbitrary (frame a -> frame b) pairs over a frame array (used for batches of clips and
+ * for sharding a clip by pair range).  out_index[p] / dup_index[p] (host arrays) give the output slot of pair p
+ * and an optional second slot to copy it to (-1 = none). */
+TEEFLOW_API int teeflow_calc_pairs(teeflow_handle h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                       int64_t frame_stride, const int32_t* pair_a, const int32_t* pair_b,
+                       const int32_t* out_index, const int32_t* dup_index, int n_pairs, float* flow_f32_dev,
+                       void* flow_f16_dev, float out_scale, void* stream);
+
+/* Same as teeflow_calc_clip with HOST buffers: copies the frames in, the flow out (the end-to-end path). */
+TEEFLOW_API int teeflow_calc_clip_host(teeflow_handle h, const void* frames_host, int dtype, int n_frames, int H, int W,
+                           float* flow_f32_host, void* flow_f16_host, float out_scale, int duplicate_last);
+
+/* OF_model.calc(I0, I1, None): two H x W host images -> H x W x 2 float32 host flow. */
+TEEFLOW_API int teeflow_calc_pair_host(teeflow_handle h, const void* I0_host, const void* I1_host, int dtype, int H, int W,
+                           float* flow_host);
+
+/* Work actually executed by the last calc: counters[p][level][3] = inner iterations, median passes, warps
+ * (int32, level 0 = finest, TEEFLOW_MAX_LEVELS levels per pair) -- needed for the roofline accounting because
+ * the inner loop exits early.  n_pairs_cap = capacity of `counters` in pairs.  Also returns the number of
+ * pyramid levels used, scheduler steps (kernel launches) of the last calc and its device time in ms. */
+TEEFLOW_API int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap, int32_t* n_levels,
+                         int64_t* n_launches, float* device_ms);
+
+/* Pyramid geometry the handle would use for an H x W image: level sizes (finest first). Returns the level count. */
+TEEFLOW_API int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEEFLOW_H_ */

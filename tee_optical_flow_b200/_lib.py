@@ -1,0 +1,75 @@
+"""ctypes binding of libteeflow.so (include/teeflow.h).  Fails loudly when the library is missing: the product
+has no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+from .exceptions import EngineUnavailableError
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libteeflow.so"
+
+TEEFLOW_MAX_LEVELS = 16
+TEEFLOW_U8, TEEFLOW_F32 = 0, 1
+ERR_BAD_ARG, ERR_BAD_SHAPE, ERR_CUDA, ERR_NCCL, ERR_STATE = -1, -2, -3, -4, -5
+
+
+class TeeflowParams(C.Structure):
+    _fields_ = [
+        ("tau", C.c_double), ("lambda_", C.c_double), ("theta", C.c_double), ("epsilon", C.c_double),
+        ("scale_step", C.c_double), ("nscales", C.c_int32), ("warps", C.c_int32),
+        ("inner_iterations", C.c_int32), ("outer_iterations", C.c_int32), ("median_filtering", C.c_int32),
+        ("max_slots", C.c_int32),
+    ]
+
+
+# every symbol include/teeflow.h declares: name -> (restype, argtypes)
+_i32p = C.POINTER(C.c_int32)
+SIGNATURES = {
+    "teeflow_default_params": (None, [C.POINTER(TeeflowParams)]),
+    "teeflow_abi_version": (C.c_int, []),
+    "teeflow_create": (C.c_int, [C.POINTER(TeeflowParams), C.c_int, C.POINTER(C.c_void_p)]),
+    "teeflow_destroy": (C.c_int, [C.c_void_p]),
+    "teeflow_set_param": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "teeflow_get_param": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_double)]),
+    "teeflow_last_error": (C.c_char_p, [C.c_void_p]),
+    "teeflow_calc_clip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
+    "teeflow_calc_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                     _i32p, _i32p, _i32p, _i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                                     C.c_void_p]),
+    "teeflow_calc_clip_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_float, C.c_int]),
+    "teeflow_calc_pair_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p]),
+    "teeflow_get_counters": (C.c_int, [C.c_void_p, _i32p, C.c_int, _i32p, C.POINTER(C.c_int64),
+                                       C.POINTER(C.c_float)]),
+    "teeflow_level_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p, _i32p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen libteeflow.so and type every entry point.  Raises EngineUnavailableError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise EngineUnavailableError(
+            f"{LIB_PATH} not found: build it with `python -m tee_optical_flow_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    try:
+        lib = C.CDLL(str(LIB_PATH))
+    except OSError as e:  # pragma: no cover
+        raise EngineUnavailableError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise EngineUnavailableError(f"{LIB_PATH} does not export {name}") from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

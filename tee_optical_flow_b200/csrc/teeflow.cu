@@ -1,0 +1,497 @@
+// teeflow.cu -- host side of libteeflow.so: the C ABI declared in include/teeflow.h.
+//
+// Replaces, for the reference's TV-L1 path only (optical_flow/calculate_optical_flow.py:564-600,627-660):
+// the cv2.optflow DualTVL1 object and the serial per-pair loop that drives it.  One handle == one GPU.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/teeflow.h"
+#include "tvl1_kernels.cuh"
+
+using namespace teeflow;
+
+static_assert(TEEFLOW_MAX_LEVELS == kMaxLevels, "ABI level count");
+
+static thread_local std::string g_last_error;
+
+struct teeflow_engine {
+    teeflow_params p;
+    int device = 0;
+    int num_sms = 0;
+    int ctas_per_sm = 1;
+    std::string err;
+    // workspace (grown on demand)
+    size_t cap_frames = 0, cap_pyr_stride = 0;
+    int cap_slots = 0;
+    size_t cap_slot_px = 0, cap_tiles = 0, cap_pairs = 0;
+    float* pyrI = nullptr;
+    float4* pyrG = nullptr;
+    float2 *U[2] = {nullptr, nullptr}, *PX[2] = {nullptr, nullptr}, *PY[2] = {nullptr, nullptr};
+    float4* COEF = nullptr;
+    Slot* slots = nullptr;     // [2][S]
+    unsigned* arrive = nullptr;
+    double* partial = nullptr;
+    int* ctl = nullptr;        // [0] next_pair, [1] pairs_done
+    int* pair_lists = nullptr; // [4][cap_pairs]
+    int* counters = nullptr;   // [cap_pairs][kMaxLevels][3]
+    int* h_done = nullptr;     // pinned
+    void* stage_in = nullptr; size_t stage_in_bytes = 0;
+    void* stage_f32 = nullptr; size_t stage_f32_bytes = 0;
+    void* stage_f16 = nullptr; size_t stage_f16_bytes = 0;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaStream_t own_stream = nullptr;
+    // last-call record
+    int last_pairs = 0, last_levels = 0;
+    long long last_launches = 0;
+    float last_ms = 0.f;
+};
+
+static int fail(teeflow_engine* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    g_last_error = buf;
+    return code;
+}
+
+#define CU_TRY(h, call)                                                                             \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(h, TEEFLOW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+static int validate_params(teeflow_engine* h, const teeflow_params& p) {
+    if (!(p.tau > 0) || !(p.lambda > 0) || !(p.theta > 0) || !(p.epsilon >= 0))
+        return fail(h, TEEFLOW_ERR_BAD_ARG, "tau, lambda, theta must be > 0 and epsilon >= 0");
+    if (!(p.scale_step > 0 && p.scale_step < 1)) return fail(h, TEEFLOW_ERR_BAD_ARG, "scale_step must be in (0,1)");
+    if (p.nscales < 1 || p.nscales > kMaxLevels) return fail(h, TEEFLOW_ERR_BAD_ARG, "nscales must be in [1,%d]", kMaxLevels);
+    if (p.warps < 1 || p.inner_iterations < 1 || p.outer_iterations < 1)
+        return fail(h, TEEFLOW_ERR_BAD_ARG, "warps, inner_iterations, outer_iterations must be >= 1");
+    if (p.median_filtering > 1 && p.median_filtering != 3 && p.median_filtering != 5)
+        return fail(h, TEEFLOW_ERR_BAD_ARG, "median_filtering must be <=1 (off), 3 or 5");
+    if (p.max_slots < 0 || p.max_slots > kMaxSlots) return fail(h, TEEFLOW_ERR_BAD_ARG, "max_slots must be in [0,%d]", kMaxSlots);
+    return TEEFLOW_OK;
+}
+
+// pyramid geometry: dsize = cvRound(size * scale_step); stop before a level with a side < 16 px (tvl1flow.cpp calc)
+static int level_geometry(const teeflow_params& p, int H, int W, int* Hs, int* Ws) {
+    Hs[0] = H; Ws[0] = W;
+    int L = 1;
+    for (int s = 1; s < p.nscales; ++s) {
+        const int w = (int)std::lrint(Ws[s - 1] * p.scale_step);
+        const int hh = (int)std::lrint(Hs[s - 1] * p.scale_step);
+        if (w < 16 || hh < 16) break;
+        Hs[s] = hh; Ws[s] = w; L = s + 1;
+    }
+    return L;
+}
+
+extern "C" {
+
+void teeflow_default_params(teeflow_params* p) {
+    if (!p) return;
+    p->tau = 0.25; p->lambda = 0.15; p->theta = 0.3; p->epsilon = 0.01; p->scale_step = 0.8;
+    p->nscales = 5; p->warps = 5; p->inner_iterations = 30; p->outer_iterations = 10; p->median_filtering = 5;
+    p->max_slots = 0;
+}
+
+int teeflow_abi_version(void) { return TEEFLOW_ABI_VERSION; }
+
+const char* teeflow_last_error(teeflow_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
+    if (!out) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "out handle pointer is NULL");
+    *out = nullptr;
+    teeflow_params pp;
+    if (p) pp = *p; else teeflow_default_params(&pp);
+    int rc = validate_params(nullptr, pp);
+    if (rc) return rc;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TEEFLOW_ERR_CUDA, "no CUDA device available (%s); teeflow has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "device %d out of range [0,%d)", device, ndev);
+    teeflow_engine* h = new (std::nothrow) teeflow_engine();
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "out of host memory");
+    h->p = pp;
+    h->device = device;
+    CU_TRY(h, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(h, cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    int occ = 0;
+    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tvl1_step_kernel, kThreads, 0));
+    if (occ < 1) { delete h; return fail(nullptr, TEEFLOW_ERR_CUDA, "tvl1_step_kernel cannot be resident on this device"); }
+    h->ctas_per_sm = occ;
+    CU_TRY(h, cudaMallocHost(&h->h_done, sizeof(int) * 4));
+    CU_TRY(h, cudaMalloc(&h->ctl, sizeof(int) * 4));
+    for (auto& ev : h->ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventCreate(&h->ev_t0));
+    CU_TRY(h, cudaEventCreate(&h->ev_t1));
+    CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    *out = h;
+    return TEEFLOW_OK;
+}
+
+int teeflow_destroy(teeflow_handle h) {
+    if (!h) return TEEFLOW_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->pyrI); cudaFree(h->pyrG);
+    for (int i = 0; i < 2; ++i) { cudaFree(h->U[i]); cudaFree(h->PX[i]); cudaFree(h->PY[i]); }
+    cudaFree(h->COEF); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
+    cudaFree(h->pair_lists); cudaFree(h->counters);
+    cudaFree(h->stage_in); cudaFree(h->stage_f32); cudaFree(h->stage_f16);
+    cudaFreeHost(h->h_done);
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+    if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return TEEFLOW_OK;
+}
+
+static double* param_slot_d(teeflow_params& p, const char* key) {
+    if (!strcmp(key, "tau")) return &p.tau;
+    if (!strcmp(key, "lambda")) return &p.lambda;
+    if (!strcmp(key, "theta")) return &p.theta;
+    if (!strcmp(key, "epsilon")) return &p.epsilon;
+    if (!strcmp(key, "scale_step")) return &p.scale_step;
+    return nullptr;
+}
+static int32_t* param_slot_i(teeflow_params& p, const char* key) {
+    if (!strcmp(key, "nscales")) return &p.nscales;
+    if (!strcmp(key, "warps")) return &p.warps;
+    if (!strcmp(key, "inner_iterations")) return &p.inner_iterations;
+    if (!strcmp(key, "outer_iterations")) return &p.outer_iterations;
+    if (!strcmp(key, "median_filtering")) return &p.median_filtering;
+    if (!strcmp(key, "max_slots")) return &p.max_slots;
+    return nullptr;
+}
+
+int teeflow_set_param(teeflow_handle h, const char* key, double value) {
+    if (!h || !key) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL handle or key");
+    teeflow_params np = h->p;
+    if (double* d = param_slot_d(np, key)) *d = value;
+    else if (int32_t* i = param_slot_i(np, key)) {
+        if (value != std::floor(value)) return fail(h, TEEFLOW_ERR_BAD_ARG, "parameter %s must be an integer", key);
+        *i = (int32_t)value;
+    } else return fail(h, TEEFLOW_ERR_BAD_ARG, "unknown parameter '%s'", key);
+    int rc = validate_params(h, np);
+    if (rc) return rc;
+    h->p = np;
+    return TEEFLOW_OK;
+}
+
+int teeflow_get_param(teeflow_handle h, const char* key, double* value) {
+    if (!h || !key || !value) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
+    if (double* d = param_slot_d(h->p, key)) { *value = *d; return TEEFLOW_OK; }
+    if (int32_t* i = param_slot_i(h->p, key)) { *value = (double)*i; return TEEFLOW_OK; }
+    return fail(h, TEEFLOW_ERR_BAD_ARG, "unknown parameter '%s'", key);
+}
+
+int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws) {
+    if (!h || !Hs || !Ws || H <= 0 || W <= 0) return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    int hs[kMaxLevels], ws[kMaxLevels];
+    const int L = level_geometry(h->p, H, W, hs, ws);
+    for (int i = 0; i < L; ++i) { Hs[i] = hs[i]; Ws[i] = ws[i]; }
+    return L;
+}
+
+}  // extern "C"
+
+template <typename T>
+static cudaError_t regrow(T*& ptr, size_t count) {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    return cudaMalloc((void**)&ptr, count * sizeof(T));
+}
+
+static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_stride, int S, size_t slot_px,
+                            size_t max_tiles, size_t n_pairs) {
+    if (n_frames * pyr_stride > h->cap_frames * h->cap_pyr_stride) {
+        CU_TRY(h, regrow(h->pyrI, n_frames * pyr_stride));
+        CU_TRY(h, regrow(h->pyrG, n_frames * pyr_stride));
+        h->cap_frames = n_frames; h->cap_pyr_stride = pyr_stride;
+    }
+    if ((size_t)S * slot_px > (size_t)h->cap_slots * h->cap_slot_px) {
+        for (int i = 0; i < 2; ++i) {
+            CU_TRY(h, regrow(h->U[i], (size_t)S * slot_px));
+            CU_TRY(h, regrow(h->PX[i], (size_t)S * slot_px));
+            CU_TRY(h, regrow(h->PY[i], (size_t)S * slot_px));
+        }
+        CU_TRY(h, regrow(h->COEF, (size_t)S * slot_px));
+        h->cap_slots = S; h->cap_slot_px = slot_px;
+    }
+    if ((size_t)S * max_tiles > h->cap_tiles) {
+        CU_TRY(h, regrow(h->partial, (size_t)S * max_tiles));
+        h->cap_tiles = (size_t)S * max_tiles;
+    }
+    if (!h->slots) {
+        CU_TRY(h, regrow(h->slots, (size_t)2 * kMaxSlots));
+        CU_TRY(h, regrow(h->arrive, (size_t)kMaxSlots));
+    }
+    if (n_pairs > h->cap_pairs) {
+        CU_TRY(h, regrow(h->pair_lists, 4 * n_pairs));
+        CU_TRY(h, regrow(h->counters, n_pairs * kMaxLevels * 3));
+        h->cap_pairs = n_pairs;
+    }
+    return TEEFLOW_OK;
+}
+
+static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                     int64_t frame_stride, const int32_t* pair_a, const int32_t* pair_b, const int32_t* out_index,
+                     const int32_t* dup_index, int n_pairs, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
+                     cudaStream_t stream) {
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (!frames_dev || !pair_a || !pair_b || !out_index || !dup_index)
+        return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL frames or pair list");
+    if (dtype != TEEFLOW_U8 && dtype != TEEFLOW_F32) return fail(h, TEEFLOW_ERR_BAD_ARG, "dtype must be TEEFLOW_U8 or TEEFLOW_F32");
+    if (H < 1 || W < 1 || n_frames < 1 || (int64_t)H * W > (1 << 28)) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "bad frame shape %dx%d", H, W);
+    if (frame_stride < (int64_t)H * W) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "frame_stride smaller than H*W");
+    if (n_pairs < 0) return fail(h, TEEFLOW_ERR_BAD_ARG, "negative pair count");
+    if (!flow_f32_dev && !flow_f16_dev) return fail(h, TEEFLOW_ERR_BAD_ARG, "no output buffer");
+    for (int i = 0; i < n_pairs; ++i)
+        if (pair_a[i] < 0 || pair_a[i] >= n_frames || pair_b[i] < 0 || pair_b[i] >= n_frames || out_index[i] < 0)
+            return fail(h, TEEFLOW_ERR_BAD_ARG, "pair %d references a frame outside [0,%d)", i, n_frames);
+    CU_TRY(h, cudaSetDevice(h->device));
+    h->last_pairs = n_pairs; h->last_launches = 0; h->last_ms = 0.f;
+    if (n_pairs == 0) return TEEFLOW_OK;
+
+    EngineParams P;
+    memset(&P, 0, sizeof(P));
+    int Hs[kMaxLevels], Ws[kMaxLevels];
+    const int L = level_geometry(h->p, H, W, Hs, Ws);
+    h->last_levels = L;
+    long long off = 0;
+    for (int l = 0; l < L; ++l) {
+        LevelGeom& g = P.lv[l];
+        g.H = Hs[l]; g.W = Ws[l];
+        g.tiles_x = (g.W + kTW - 1) / kTW; g.tiles_y = (g.H + kTH - 1) / kTH; g.ntiles = g.tiles_x * g.tiles_y;
+        g.pyr_off = off;
+        off += ((long long)g.H * g.W + 63) / 64 * 64;
+        g.scaled_eps = (float)(h->p.epsilon * h->p.epsilon * (double)(g.H * g.W));
+        if (l + 1 < L) {
+            // resize(u(l+1), u(l), size(l)): inv_scale = dsize/ssize; scale = 1./inv_scale (imgproc/resize.cpp)
+            g.up_sx = 1.0 / ((double)Ws[l] / (double)Ws[l + 1]);
+            g.up_sy = 1.0 / ((double)Hs[l] / (double)Hs[l + 1]);
+        }
+    }
+    const int S = std::min(h->p.max_slots > 0 ? h->p.max_slots : 64, std::min(n_pairs, kMaxSlots));
+    P.L = L; P.S = S; P.n_pairs = n_pairs;
+    P.warps = h->p.warps; P.inner = h->p.inner_iterations; P.outer = h->p.outer_iterations; P.median = h->p.median_filtering;
+    P.l_t = (float)(h->p.lambda * h->p.theta);
+    P.theta = (float)h->p.theta;
+    P.taut = (float)(h->p.tau / h->p.theta);
+    P.up_mul = (float)(1.0 / h->p.scale_step);
+    P.out_scale = out_scale;
+    P.frame_pyr_stride = off;
+    P.slot_px = ((long long)H * W + 63) / 64 * 64;
+    P.max_tiles = P.lv[0].ntiles;
+
+    int rc = ensure_workspace(h, (size_t)n_frames, (size_t)off, S, (size_t)P.slot_px, (size_t)P.max_tiles, (size_t)n_pairs);
+    if (rc) return rc;
+    P.pyrI = h->pyrI; P.pyrG = h->pyrG;
+    for (int i = 0; i < 2; ++i) { P.U[i] = h->U[i]; P.PX[i] = h->PX[i]; P.PY[i] = h->PY[i]; P.slots[i] = h->slots + (size_t)i * kMaxSlots; }
+    P.COEF = h->COEF; P.arrive = h->arrive; P.partial = h->partial;
+    P.next_pair = h->ctl; P.pairs_done = h->ctl + 1;
+    P.pair_a = h->pair_lists; P.pair_b = h->pair_lists + h->cap_pairs;
+    P.out_index = h->pair_lists + 2 * h->cap_pairs; P.dup_index = h->pair_lists + 3 * h->cap_pairs;
+    P.counters_out = h->counters;
+    P.flow_f32 = (float2*)flow_f32_dev;
+    P.flow_f16 = (uint32_t*)flow_f16_dev;
+
+    CU_TRY(h, cudaEventRecord(h->ev_t0, stream));
+    // pair lists (small) -- pageable host memory: the copies are staged by the runtime before the call returns
+    CU_TRY(h, cudaMemcpyAsync((void*)P.pair_a, pair_a, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream));
+    CU_TRY(h, cudaMemcpyAsync((void*)P.pair_b, pair_b, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream));
+    CU_TRY(h, cudaMemcpyAsync((void*)P.out_index, out_index, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream));
+    CU_TRY(h, cudaMemcpyAsync((void*)P.dup_index, dup_index, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream));
+
+    // ---- image pyramid + packed gradients, once per frame
+    {
+        const int npx = H * W;
+        dim3 g0((unsigned)std::min((npx + 255) / 256, 1024), (unsigned)n_frames);
+        pyr_level0_kernel<<<g0, 256, 0, stream>>>(frames_dev, dtype, (long long)frame_stride, n_frames, npx, h->pyrI, off);
+        const dim3 blk(32, 8);
+        for (int l = 0; l < L; ++l) {
+            const LevelGeom& g = P.lv[l];
+            if (l > 0) {
+                const LevelGeom& s = P.lv[l - 1];
+                dim3 grd((g.W + 31) / 32, (g.H + 7) / 8, (unsigned)n_frames);
+                pyr_down_kernel<<<grd, blk, 0, stream>>>(h->pyrI, off, n_frames, s.pyr_off, s.H, s.W, g.pyr_off, g.H, g.W,
+                                                         1.0 / h->p.scale_step);
+            }
+            dim3 grd((g.W + 31) / 32, (g.H + 7) / 8, (unsigned)n_frames);
+            pyr_pack_kernel<<<grd, blk, 0, stream>>>(h->pyrI, h->pyrG, off, n_frames, g.pyr_off, g.H, g.W);
+        }
+        CU_TRY(h, cudaGetLastError());
+    }
+
+    // ---- slot table: the first S pairs start at the coarsest level, parity 0
+    {
+        std::vector<Slot> init((size_t)kMaxSlots);
+        memset(init.data(), 0, sizeof(Slot) * init.size());
+        for (int s = 0; s < kMaxSlots; ++s) {
+            Slot& sl = init[s];
+            sl.pair = -1; sl.phase = PH_IDLE;
+            if (s < S) { sl.pair = s; sl.phase = PH_LEVEL_INIT; sl.level = L - 1; sl.error = FLT_MAX; }
+        }
+        CU_TRY(h, cudaMemcpyAsync(h->slots, init.data(), sizeof(Slot) * kMaxSlots, cudaMemcpyHostToDevice, stream));
+        CU_TRY(h, cudaMemsetAsync(h->arrive, 0, sizeof(unsigned) * kMaxSlots, stream));
+        const int ctl0[4] = {S, 0, 0, 0};
+        CU_TRY(h, cudaMemcpyAsync(h->ctl, ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, stream));
+        CU_TRY(h, cudaStreamSynchronize(stream));  // `init` / ctl0 / pair lists are host temporaries
+    }
+
+    // ---- super-steps.  The host keeps two chunks of launches in flight and polls the done counter of the
+    // chunk before; finished slots make their CTAs exit at once, so an over-issued launch costs microseconds.
+    const int grid = h->num_sms * h->ctas_per_sm;
+    const int chunk = 16;
+    // upper bound on steps per pair: per level 1 init + warps * (1 + outer * (1 + inner)), + 1 final
+    const long long steps_per_pair = (long long)L * (1 + (long long)h->p.warps * (1 + (long long)h->p.outer_iterations * (1 + h->p.inner_iterations))) + 1;
+    const long long max_steps = steps_per_pair * ((n_pairs + S - 1) / S + 1) + 2 * chunk;
+    long long step = 0;
+    int pending = 0;  // chunks whose done-counter copy has been issued but not yet checked
+    bool done = false;
+    volatile int* hd = h->h_done;
+    hd[0] = hd[1] = 0;
+    while (!done) {
+        if (step > max_steps) return fail(h, TEEFLOW_ERR_STATE, "scheduler exceeded %lld steps", max_steps);
+        for (int k = 0; k < chunk; ++k, ++step)
+            tvl1_step_kernel<<<grid, kThreads, 0, stream>>>(P, (int)(step & 1));
+        CU_TRY(h, cudaGetLastError());
+        const int which = (int)((step / chunk) & 1);
+        CU_TRY(h, cudaMemcpyAsync((void*)(hd + which), h->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CU_TRY(h, cudaEventRecord(h->ev[which], stream));
+        if (++pending == 2) {
+            const int prev = which ^ 1;
+            CU_TRY(h, cudaEventSynchronize(h->ev[prev]));
+            --pending;
+            if (hd[prev] >= n_pairs) done = true;
+        }
+    }
+    CU_TRY(h, cudaEventRecord(h->ev_t1, stream));
+    CU_TRY(h, cudaStreamSynchronize(stream));
+    if (hd[0] < n_pairs && hd[1] < n_pairs) {
+        // the last issued chunk may be the one that finished the work
+        int d = 0;
+        CU_TRY(h, cudaMemcpy(&d, h->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost));
+        if (d < n_pairs) return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", d, n_pairs);
+    }
+    CU_TRY(h, cudaEventElapsedTime(&h->last_ms, h->ev_t0, h->ev_t1));
+    h->last_launches = step;
+    return TEEFLOW_OK;
+}
+
+extern "C" {
+
+int teeflow_calc_pairs(teeflow_handle h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                       int64_t frame_stride, const int32_t* pair_a, const int32_t* pair_b, const int32_t* out_index,
+                       const int32_t* dup_index, int n_pairs, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
+                       void* stream) {
+    return run_pairs(h, frames_dev, dtype, n_frames, H, W, frame_stride, pair_a, pair_b, out_index, dup_index, n_pairs,
+                     flow_f32_dev, flow_f16_dev, out_scale, (cudaStream_t)stream);
+}
+
+int teeflow_calc_clip(teeflow_handle h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                      int64_t frame_stride, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
+                      int duplicate_last, void* stream) {
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (n_frames < 2) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "a clip needs at least 2 frames, got %d", n_frames);
+    const int n_pairs = n_frames - 1;
+    std::vector<int32_t> a(n_pairs), b(n_pairs), o(n_pairs), d(n_pairs, -1);
+    for (int i = 0; i < n_pairs; ++i) { a[i] = i; b[i] = i + 1; o[i] = i; }
+    if (duplicate_last) d[n_pairs - 1] = n_pairs;
+    return run_pairs(h, frames_dev, dtype, n_frames, H, W, frame_stride, a.data(), b.data(), o.data(), d.data(), n_pairs,
+                     flow_f32_dev, flow_f16_dev, out_scale, (cudaStream_t)stream);
+}
+
+static int ensure_stage(teeflow_engine* h, void*& ptr, size_t& cap, size_t bytes) {
+    if (bytes > cap) {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        CU_TRY(h, cudaMalloc(&ptr, bytes));
+        cap = bytes;
+    }
+    return TEEFLOW_OK;
+}
+
+int teeflow_calc_clip_host(teeflow_handle h, const void* frames_host, int dtype, int n_frames, int H, int W,
+                           float* flow_f32_host, void* flow_f16_host, float out_scale, int duplicate_last) {
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (!frames_host) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL frames");
+    if (n_frames < 2 || H < 1 || W < 1) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "bad clip shape");
+    if (dtype != TEEFLOW_U8 && dtype != TEEFLOW_F32) return fail(h, TEEFLOW_ERR_BAD_ARG, "dtype must be TEEFLOW_U8 or TEEFLOW_F32");
+    if (!flow_f32_host && !flow_f16_host) return fail(h, TEEFLOW_ERR_BAD_ARG, "no output buffer");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t npx = (size_t)H * W;
+    const size_t esz = dtype == TEEFLOW_U8 ? 1 : 4;
+    const size_t n_out = (size_t)(n_frames - 1) + (duplicate_last ? 1 : 0);
+    int rc;
+    if ((rc = ensure_stage(h, h->stage_in, h->stage_in_bytes, npx * esz * n_frames))) return rc;
+    if (flow_f32_host && (rc = ensure_stage(h, h->stage_f32, h->stage_f32_bytes, n_out * npx * 8))) return rc;
+    if (flow_f16_host && (rc = ensure_stage(h, h->stage_f16, h->stage_f16_bytes, n_out * npx * 4))) return rc;
+    cudaStream_t st = h->own_stream;
+    CU_TRY(h, cudaMemcpyAsync(h->stage_in, frames_host, npx * esz * n_frames, cudaMemcpyHostToDevice, st));
+    rc = teeflow_calc_clip(h, h->stage_in, dtype, n_frames, H, W, (int64_t)npx, flow_f32_host ? (float*)h->stage_f32 : nullptr,
+                           flow_f16_host ? h->stage_f16 : nullptr, out_scale, duplicate_last, (void*)st);
+    if (rc) return rc;
+    if (flow_f32_host) CU_TRY(h, cudaMemcpyAsync(flow_f32_host, h->stage_f32, n_out * npx * 8, cudaMemcpyDeviceToHost, st));
+    if (flow_f16_host) CU_TRY(h, cudaMemcpyAsync(flow_f16_host, h->stage_f16, n_out * npx * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    return TEEFLOW_OK;
+}
+
+int teeflow_calc_pair_host(teeflow_handle h, const void* I0_host, const void* I1_host, int dtype, int H, int W,
+                           float* flow_host) {
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (!I0_host || !I1_host || !flow_host) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL image or output");
+    if (H < 1 || W < 1) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "bad image shape");
+    if (dtype != TEEFLOW_U8 && dtype != TEEFLOW_F32) return fail(h, TEEFLOW_ERR_BAD_ARG, "dtype must be TEEFLOW_U8 or TEEFLOW_F32");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t npx = (size_t)H * W;
+    const size_t esz = dtype == TEEFLOW_U8 ? 1 : 4;
+    int rc;
+    if ((rc = ensure_stage(h, h->stage_in, h->stage_in_bytes, npx * esz * 2))) return rc;
+    if ((rc = ensure_stage(h, h->stage_f32, h->stage_f32_bytes, npx * 8))) return rc;
+    cudaStream_t st = h->own_stream;
+    CU_TRY(h, cudaMemcpyAsync(h->stage_in, I0_host, npx * esz, cudaMemcpyHostToDevice, st));
+    CU_TRY(h, cudaMemcpyAsync((char*)h->stage_in + npx * esz, I1_host, npx * esz, cudaMemcpyHostToDevice, st));
+    rc = teeflow_calc_clip(h, h->stage_in, dtype, 2, H, W, (int64_t)npx, (float*)h->stage_f32, nullptr, 1.0f, 0, (void*)st);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(flow_host, h->stage_f32, npx * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    return TEEFLOW_OK;
+}
+
+int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap, int32_t* n_levels, int64_t* n_launches,
+                         float* device_ms) {
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (n_levels) *n_levels = h->last_levels;
+    if (n_launches) *n_launches = h->last_launches;
+    if (device_ms) *device_ms = h->last_ms;
+    if (counters) {
+        if (n_pairs_cap < h->last_pairs) return fail(h, TEEFLOW_ERR_BAD_ARG, "counter buffer holds %d pairs, need %d", n_pairs_cap, h->last_pairs);
+        CU_TRY(h, cudaSetDevice(h->device));
+        if (h->last_pairs > 0)
+            CU_TRY(h, cudaMemcpy(counters, h->counters, sizeof(int) * (size_t)h->last_pairs * kMaxLevels * 3, cudaMemcpyDeviceToHost));
+    }
+    return h->last_pairs;
+}
+
+}  // extern "C"

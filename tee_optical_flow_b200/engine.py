@@ -1,0 +1,252 @@
+"""TVL1Engine -- the B200 TV-L1 solver behind the reference's operator interface.
+
+The reference selects its optical-flow operator by the string ``OF_algo`` and then only ever calls
+``OF_model.setLambda(x)`` and ``OF_model.calc(I0, I1, None)`` on it
+(optical_flow/calculate_optical_flow.py:564-578, 627-646).  ``TVL1Engine`` has that duck type (plus the other
+OpenCV-named setters/getters of ``cv2.optflow.DualTVL1OpticalFlow``), so it can be handed to the reference's
+``calculate_optical_flow(..., OF_model=engine)`` unchanged, and adds the batched ``calc_clip`` that solves all
+frame pairs of a clip concurrently on the GPU.
+
+All arithmetic happens in libteeflow.so (hand-written sm_100a CUDA, include/teeflow.h).  PyTorch is used only
+for device buffers and streams.  No CPU fallback: without the library or a GPU this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from .exceptions import EngineUnavailableError, OpticalFlowCalculationError
+
+_PARAM_KEYS = {
+    "tau": "tau", "lambda_": "lambda", "theta": "theta", "epsilon": "epsilon", "scale_step": "scale_step",
+    "nscales": "nscales", "warps": "warps", "inner_iterations": "inner_iterations",
+    "outer_iterations": "outer_iterations", "median_filtering": "median_filtering", "max_slots": "max_slots",
+}
+
+
+def _dtype_code(dt) -> int:
+    if dt == np.uint8:
+        return _lib.TEEFLOW_U8
+    if dt == np.float32:
+        return _lib.TEEFLOW_F32
+    # same restriction as OpenCV: CV_8UC1 or CV_32FC1 (cv2.error in the reference)
+    raise OpticalFlowCalculationError(f"TV-L1 input must be uint8 or float32, got {dt}")
+
+
+class TVL1Engine:
+    """Drop-in for ``cv2.optflow.createOptFlow_DualTVL1()`` (calculate_optical_flow.py:577)."""
+
+    def __init__(self, device: Optional[int] = None, **params):
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        p = _lib.TeeflowParams()
+        self._lib.teeflow_default_params(C.byref(p))
+        for k, v in params.items():
+            if k not in _PARAM_KEYS:
+                raise TypeError(f"unknown TV-L1 parameter {k!r}")
+            setattr(p, k, v)
+        if device is None:
+            device = 0
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    device = torch.cuda.current_device()
+            except ImportError:  # pragma: no cover
+                pass
+        self.device = int(device)
+        rc = self._lib.teeflow_create(C.byref(p), self.device, C.byref(self._h))
+        if rc != 0:
+            msg = (self._lib.teeflow_last_error(None) or b"").decode()
+            self._h = C.c_void_p()
+            if rc == _lib.ERR_CUDA:
+                raise EngineUnavailableError(msg)
+            raise OpticalFlowCalculationError(f"teeflow_create failed ({rc}): {msg}")
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.teeflow_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def _check(self, rc: int):
+        if rc < 0:
+            msg = (self._lib.teeflow_last_error(self._h) or b"").decode()
+            raise OpticalFlowCalculationError(f"libteeflow error {rc}: {msg}")
+        return rc
+
+    # ------------------------------------------------------------------ parameters (OpenCV names)
+    def _set(self, key, v):
+        self._check(self._lib.teeflow_set_param(self._h, key.encode(), float(v)))
+
+    def _get(self, key):
+        out = C.c_double()
+        self._check(self._lib.teeflow_get_param(self._h, key.encode(), C.byref(out)))
+        return out.value
+
+    def setLambda(self, v): self._set("lambda", v)
+    def getLambda(self): return self._get("lambda")
+    def setTau(self, v): self._set("tau", v)
+    def getTau(self): return self._get("tau")
+    def setTheta(self, v): self._set("theta", v)
+    def getTheta(self): return self._get("theta")
+    def setEpsilon(self, v): self._set("epsilon", v)
+    def getEpsilon(self): return self._get("epsilon")
+    def setScaleStep(self, v): self._set("scale_step", v)
+    def getScaleStep(self): return self._get("scale_step")
+    def setScalesNumber(self, v): self._set("nscales", v)
+    def getScalesNumber(self): return int(self._get("nscales"))
+    def setWarpingsNumber(self, v): self._set("warps", v)
+    def getWarpingsNumber(self): return int(self._get("warps"))
+    def setInnerIterations(self, v): self._set("inner_iterations", v)
+    def getInnerIterations(self): return int(self._get("inner_iterations"))
+    def setOuterIterations(self, v): self._set("outer_iterations", v)
+    def getOuterIterations(self): return int(self._get("outer_iterations"))
+    def setMedianFiltering(self, v): self._set("median_filtering", v)
+    def getMedianFiltering(self): return int(self._get("median_filtering"))
+
+    def setGamma(self, v):
+        if float(v) != 0.0:
+            raise OpticalFlowCalculationError("gamma != 0 is not supported (the reference never sets it)")
+
+    def getGamma(self): return 0.0
+
+    def setUseInitialFlow(self, v):
+        if v:
+            raise OpticalFlowCalculationError("useInitialFlow is not supported (the reference never sets it)")
+
+    def getUseInitialFlow(self): return False
+
+    # ------------------------------------------------------------------ OF_model.calc (one pair, host arrays)
+    def calc(self, I0, I1, flow=None) -> np.ndarray:
+        """``OF_model.calc(saliency_1, saliency_2, None)`` (calculate_optical_flow.py:642): two (H, W) uint8 or
+        float32 images -> (H, W, 2) float32, channel 0 = x displacement, 1 = y."""
+        I0 = np.ascontiguousarray(I0)
+        I1 = np.ascontiguousarray(I1)
+        if I0.ndim != 2 or I0.shape != I1.shape or I0.dtype != I1.dtype:
+            raise OpticalFlowCalculationError("I0 and I1 must be 2-D arrays of identical shape and dtype")
+        code = _dtype_code(I0.dtype)
+        H, W = I0.shape
+        out = np.empty((H, W, 2), np.float32)
+        self._check(self._lib.teeflow_calc_pair_host(self._h, I0.ctypes.data, I1.ctypes.data, code, H, W,
+                                                     out.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ all pairs of a clip
+    def calc_clip(self, frames, out_scale: float = 1.0, duplicate_last: bool = True, want_f32: bool = True,
+                  want_f16: bool = False):
+        """Flow of every consecutive pair of ``frames`` (N, H, W) -- the reference's pair loop
+        (calculate_optical_flow.py:584-600) in one call.
+
+        numpy frames  -> host path (H2D and D2H inside the call), numpy results.
+        torch CUDA tensor -> device path, torch results on the same device.
+        Returns (flow_f32 or None, flow_f16 or None), each (N_out, H, W, 2) with N_out = N-1 (+1 when
+        ``duplicate_last``: the reference appends a copy of the last flow, :599).
+        """
+        if isinstance(frames, np.ndarray):
+            return self._calc_clip_host(frames, out_scale, duplicate_last, want_f32, want_f16)
+        return self._calc_clip_device(frames, out_scale, duplicate_last, want_f32, want_f16)
+
+    def _calc_clip_host(self, frames, out_scale, duplicate_last, want_f32, want_f16):
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim != 3:
+            raise OpticalFlowCalculationError("frames must be (N, H, W)")
+        code = _dtype_code(frames.dtype)
+        N, H, W = frames.shape
+        n_out = N - 1 + (1 if duplicate_last else 0)
+        f32 = np.empty((n_out, H, W, 2), np.float32) if want_f32 else None
+        f16 = np.empty((n_out, H, W, 2), np.float16) if want_f16 else None
+        self._check(self._lib.teeflow_calc_clip_host(
+            self._h, frames.ctypes.data, code, N, H, W, f32.ctypes.data if want_f32 else None,
+            f16.ctypes.data if want_f16 else None, float(np.float32(out_scale)), int(duplicate_last)))
+        return f32, f16
+
+    def _calc_clip_device(self, frames, out_scale, duplicate_last, want_f32, want_f16, out_f32=None, out_f16=None):
+        import torch
+        if not (isinstance(frames, torch.Tensor) and frames.is_cuda):
+            raise OpticalFlowCalculationError("frames must be a numpy array or a CUDA torch tensor")
+        if frames.device.index != self.device:
+            raise OpticalFlowCalculationError(f"frames live on cuda:{frames.device.index}, engine on cuda:{self.device}")
+        if frames.dim() != 3:
+            raise OpticalFlowCalculationError("frames must be (N, H, W)")
+        if frames.dtype == torch.uint8:
+            code = _lib.TEEFLOW_U8
+        elif frames.dtype == torch.float32:
+            code = _lib.TEEFLOW_F32
+        else:
+            raise OpticalFlowCalculationError(f"TV-L1 input must be uint8 or float32, got {frames.dtype}")
+        frames = frames.contiguous()
+        N, H, W = frames.shape
+        n_out = N - 1 + (1 if duplicate_last else 0)
+        f32 = out_f32 if out_f32 is not None else (
+            torch.empty((n_out, H, W, 2), dtype=torch.float32, device=frames.device) if want_f32 else None)
+        f16 = out_f16 if out_f16 is not None else (
+            torch.empty((n_out, H, W, 2), dtype=torch.float16, device=frames.device) if want_f16 else None)
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        self._check(self._lib.teeflow_calc_clip(
+            self._h, frames.data_ptr(), code, N, H, W, H * W, f32.data_ptr() if f32 is not None else None,
+            f16.data_ptr() if f16 is not None else None, float(np.float32(out_scale)), int(duplicate_last),
+            C.c_void_p(stream)))
+        return f32, f16
+
+    def calc_pairs_device(self, frames, pair_a, pair_b, out_index=None, dup_index=None, n_out=None,
+                          out_scale: float = 1.0, want_f32: bool = True, want_f16: bool = False):
+        """Generic form: arbitrary (frame a -> frame b) pairs over a CUDA frame tensor (N, H, W); used for
+        batches of clips and for sharding a clip by pair range."""
+        import torch
+        pair_a = np.ascontiguousarray(pair_a, np.int32)
+        pair_b = np.ascontiguousarray(pair_b, np.int32)
+        n_pairs = len(pair_a)
+        out_index = np.arange(n_pairs, dtype=np.int32) if out_index is None else np.ascontiguousarray(out_index, np.int32)
+        dup_index = np.full(n_pairs, -1, np.int32) if dup_index is None else np.ascontiguousarray(dup_index, np.int32)
+        if n_out is None:
+            n_out = int(max(out_index.max(initial=-1), dup_index.max(initial=-1)) + 1)
+        frames = frames.contiguous()
+        N, H, W = frames.shape
+        code = _lib.TEEFLOW_U8 if frames.dtype == torch.uint8 else _lib.TEEFLOW_F32
+        f32 = torch.empty((n_out, H, W, 2), dtype=torch.float32, device=frames.device) if want_f32 else None
+        f16 = torch.empty((n_out, H, W, 2), dtype=torch.float16, device=frames.device) if want_f16 else None
+        ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        self._check(self._lib.teeflow_calc_pairs(
+            self._h, frames.data_ptr(), code, N, H, W, H * W, ip(pair_a), ip(pair_b), ip(out_index), ip(dup_index),
+            n_pairs, f32.data_ptr() if f32 is not None else None, f16.data_ptr() if f16 is not None else None,
+            float(np.float32(out_scale)), C.c_void_p(stream)))
+        return f32, f16
+
+    # ------------------------------------------------------------------ accounting
+    def last_counters(self) -> Tuple[np.ndarray, dict]:
+        """(counters[n_pairs, n_levels, 3] = inner iterations / median passes / warps executed per level,
+        info dict) of the last calc -- the inputs of the roofline accounting."""
+        nl, nlaunch, ms = C.c_int32(), C.c_int64(), C.c_float()
+        n = self._check(self._lib.teeflow_get_counters(self._h, None, 0, C.byref(nl), C.byref(nlaunch), C.byref(ms)))
+        buf = np.zeros((max(n, 1), _lib.TEEFLOW_MAX_LEVELS, 3), np.int32)
+        self._check(self._lib.teeflow_get_counters(self._h, buf.ctypes.data_as(C.POINTER(C.c_int32)), max(n, 1),
+                                                   C.byref(nl), C.byref(nlaunch), C.byref(ms)))
+        return buf[:n, :nl.value].copy(), dict(n_levels=nl.value, launches=nlaunch.value, device_ms=ms.value)
+
+    def level_sizes(self, H: int, W: int):
+        hs = (C.c_int32 * _lib.TEEFLOW_MAX_LEVELS)()
+        ws = (C.c_int32 * _lib.TEEFLOW_MAX_LEVELS)()
+        L = self._check(self._lib.teeflow_level_sizes(self._h, H, W, hs, ws))
+        return [(hs[i], ws[i]) for i in range(L)]
+
+
+def createOptFlow_DualTVL1(**params) -> TVL1Engine:
+    """Spelling of the reference's factory call (cv2.optflow.createOptFlow_DualTVL1, :577)."""
+    return TVL1Engine(**params)
