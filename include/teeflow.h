@@ -108,12 +108,26 @@ TEEFLOW_API int teeflow_calc_clip_host(teeflow_handle h, const void* frames_host
 TEEFLOW_API int teeflow_calc_pair_host(teeflow_handle h, const void* I0_host, const void* I1_host, int dtype, int H, int W,
                            float* flow_host);
 
+/* Timing / launch record of the last calc (device times from CUDA events on the caller's stream). */
+typedef struct {
+    int32_t n_pairs;          /* frame pairs solved */
+    int32_t n_levels;         /* pyramid levels used */
+    int32_t n_slots;          /* pairs in flight */
+    int32_t grid_ctas;        /* persistent CTAs per solver launch */
+    int64_t solver_launches;  /* tvl1_step_kernel launches (scheduler super-steps, incl. over-issued ones) */
+    int64_t kernel_launches;  /* all kernels launched by the call (pyramid + solver) */
+    float device_ms;          /* whole call on the device */
+    float pyramid_ms;         /* pyramid + gradient pack kernels */
+    float solver_ms;          /* first to last solver launch */
+    float reserved;
+} teeflow_stats;
+
 /* Work actually executed by the last calc: counters[p][level][3] = inner iterations, median passes, warps
  * (int32, level 0 = finest, TEEFLOW_MAX_LEVELS levels per pair) -- needed for the roofline accounting because
- * the inner loop exits early.  n_pairs_cap = capacity of `counters` in pairs.  Also returns the number of
- * pyramid levels used, scheduler steps (kernel launches) of the last calc and its device time in ms. */
-TEEFLOW_API int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap, int32_t* n_levels,
-                         int64_t* n_launches, float* device_ms);
+ * the inner loop exits early.  n_pairs_cap = capacity of `counters` in pairs (counters may be NULL).
+ * Returns the number of pairs of the last calc. */
+TEEFLOW_API int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap);
+TEEFLOW_API int teeflow_get_stats(teeflow_handle h, teeflow_stats* out);
 
 /* Pyramid geometry the handle would use for an H x W image: level sizes (finest first). Returns the level count. */
 TEEFLOW_API int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws);

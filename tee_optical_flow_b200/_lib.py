@@ -24,6 +24,14 @@ class TeeflowParams(C.Structure):
     ]
 
 
+class TeeflowStats(C.Structure):
+    _fields_ = [
+        ("n_pairs", C.c_int32), ("n_levels", C.c_int32), ("n_slots", C.c_int32), ("grid_ctas", C.c_int32),
+        ("solver_launches", C.c_int64), ("kernel_launches", C.c_int64), ("device_ms", C.c_float),
+        ("pyramid_ms", C.c_float), ("solver_ms", C.c_float), ("reserved", C.c_float),
+    ]
+
+
 # every symbol include/teeflow.h declares: name -> (restype, argtypes)
 _i32p = C.POINTER(C.c_int32)
 SIGNATURES = {
@@ -43,8 +51,8 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p, C.c_float, C.c_int]),
     "teeflow_calc_pair_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p]),
-    "teeflow_get_counters": (C.c_int, [C.c_void_p, _i32p, C.c_int, _i32p, C.POINTER(C.c_int64),
-                                       C.POINTER(C.c_float)]),
+    "teeflow_get_counters": (C.c_int, [C.c_void_p, _i32p, C.c_int]),
+    "teeflow_get_stats": (C.c_int, [C.c_void_p, C.POINTER(TeeflowStats)]),
     "teeflow_level_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p, _i32p]),
 }
 

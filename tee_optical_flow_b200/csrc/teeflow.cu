@@ -47,12 +47,10 @@ struct teeflow_engine {
     void* stage_f32 = nullptr; size_t stage_f32_bytes = 0;
     void* stage_f16 = nullptr; size_t stage_f16_bytes = 0;
     cudaEvent_t ev[2] = {nullptr, nullptr};
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_tp = nullptr;
     cudaStream_t own_stream = nullptr;
     // last-call record
-    int last_pairs = 0, last_levels = 0;
-    long long last_launches = 0;
-    float last_ms = 0.f;
+    teeflow_stats st{};
 };
 
 static int fail(teeflow_engine* h, int code, const char* fmt, ...) {
@@ -143,6 +141,7 @@ int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
     for (auto& ev : h->ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU_TRY(h, cudaEventCreate(&h->ev_t0));
     CU_TRY(h, cudaEventCreate(&h->ev_t1));
+    CU_TRY(h, cudaEventCreate(&h->ev_tp));
     CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     *out = h;
     return TEEFLOW_OK;
@@ -160,6 +159,7 @@ int teeflow_destroy(teeflow_handle h) {
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+    if (h->ev_tp) cudaEventDestroy(h->ev_tp);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return TEEFLOW_OK;
@@ -269,14 +269,15 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         if (pair_a[i] < 0 || pair_a[i] >= n_frames || pair_b[i] < 0 || pair_b[i] >= n_frames || out_index[i] < 0)
             return fail(h, TEEFLOW_ERR_BAD_ARG, "pair %d references a frame outside [0,%d)", i, n_frames);
     CU_TRY(h, cudaSetDevice(h->device));
-    h->last_pairs = n_pairs; h->last_launches = 0; h->last_ms = 0.f;
+    memset(&h->st, 0, sizeof(h->st));
+    h->st.n_pairs = n_pairs;
     if (n_pairs == 0) return TEEFLOW_OK;
 
     EngineParams P;
     memset(&P, 0, sizeof(P));
     int Hs[kMaxLevels], Ws[kMaxLevels];
     const int L = level_geometry(h->p, H, W, Hs, Ws);
-    h->last_levels = L;
+    h->st.n_levels = L;
     long long off = 0;
     for (int l = 0; l < L; ++l) {
         LevelGeom& g = P.lv[l];
@@ -340,6 +341,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
             pyr_pack_kernel<<<grd, blk, 0, stream>>>(h->pyrI, h->pyrG, off, n_frames, g.pyr_off, g.H, g.W);
         }
         CU_TRY(h, cudaGetLastError());
+        h->st.kernel_launches = 1 + 2 * (long long)L - 1;
     }
 
     // ---- slot table: the first S pairs start at the coarsest level, parity 0
@@ -356,6 +358,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         const int ctl0[4] = {S, 0, 0, 0};
         CU_TRY(h, cudaMemcpyAsync(h->ctl, ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, stream));
         CU_TRY(h, cudaStreamSynchronize(stream));  // `init` / ctl0 / pair lists are host temporaries
+        CU_TRY(h, cudaEventRecord(h->ev_tp, stream));
     }
 
     // ---- super-steps.  The host keeps two chunks of launches in flight and polls the done counter of the
@@ -393,8 +396,13 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         CU_TRY(h, cudaMemcpy(&d, h->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost));
         if (d < n_pairs) return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", d, n_pairs);
     }
-    CU_TRY(h, cudaEventElapsedTime(&h->last_ms, h->ev_t0, h->ev_t1));
-    h->last_launches = step;
+    CU_TRY(h, cudaEventElapsedTime(&h->st.device_ms, h->ev_t0, h->ev_t1));
+    CU_TRY(h, cudaEventElapsedTime(&h->st.pyramid_ms, h->ev_t0, h->ev_tp));
+    CU_TRY(h, cudaEventElapsedTime(&h->st.solver_ms, h->ev_tp, h->ev_t1));
+    h->st.solver_launches = step;
+    h->st.kernel_launches += step;
+    h->st.n_slots = S;
+    h->st.grid_ctas = grid;
     return TEEFLOW_OK;
 }
 
@@ -479,19 +487,22 @@ int teeflow_calc_pair_host(teeflow_handle h, const void* I0_host, const void* I1
     return TEEFLOW_OK;
 }
 
-int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap, int32_t* n_levels, int64_t* n_launches,
-                         float* device_ms) {
+int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap) {
     if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
-    if (n_levels) *n_levels = h->last_levels;
-    if (n_launches) *n_launches = h->last_launches;
-    if (device_ms) *device_ms = h->last_ms;
+    const int n = h->st.n_pairs;
     if (counters) {
-        if (n_pairs_cap < h->last_pairs) return fail(h, TEEFLOW_ERR_BAD_ARG, "counter buffer holds %d pairs, need %d", n_pairs_cap, h->last_pairs);
+        if (n_pairs_cap < n) return fail(h, TEEFLOW_ERR_BAD_ARG, "counter buffer holds %d pairs, need %d", n_pairs_cap, n);
         CU_TRY(h, cudaSetDevice(h->device));
-        if (h->last_pairs > 0)
-            CU_TRY(h, cudaMemcpy(counters, h->counters, sizeof(int) * (size_t)h->last_pairs * kMaxLevels * 3, cudaMemcpyDeviceToHost));
+        if (n > 0)
+            CU_TRY(h, cudaMemcpy(counters, h->counters, sizeof(int) * (size_t)n * kMaxLevels * 3, cudaMemcpyDeviceToHost));
     }
-    return h->last_pairs;
+    return n;
+}
+
+int teeflow_get_stats(teeflow_handle h, teeflow_stats* out) {
+    if (!h || !out) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
+    *out = h->st;
+    return TEEFLOW_OK;
 }
 
 }  // extern "C"

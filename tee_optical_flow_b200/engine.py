@@ -233,12 +233,13 @@ class TVL1Engine:
     def last_counters(self) -> Tuple[np.ndarray, dict]:
         """(counters[n_pairs, n_levels, 3] = inner iterations / median passes / warps executed per level,
         info dict) of the last calc -- the inputs of the roofline accounting."""
-        nl, nlaunch, ms = C.c_int32(), C.c_int64(), C.c_float()
-        n = self._check(self._lib.teeflow_get_counters(self._h, None, 0, C.byref(nl), C.byref(nlaunch), C.byref(ms)))
+        st = _lib.TeeflowStats()
+        self._check(self._lib.teeflow_get_stats(self._h, C.byref(st)))
+        n = st.n_pairs
         buf = np.zeros((max(n, 1), _lib.TEEFLOW_MAX_LEVELS, 3), np.int32)
-        self._check(self._lib.teeflow_get_counters(self._h, buf.ctypes.data_as(C.POINTER(C.c_int32)), max(n, 1),
-                                                   C.byref(nl), C.byref(nlaunch), C.byref(ms)))
-        return buf[:n, :nl.value].copy(), dict(n_levels=nl.value, launches=nlaunch.value, device_ms=ms.value)
+        self._check(self._lib.teeflow_get_counters(self._h, buf.ctypes.data_as(C.POINTER(C.c_int32)), max(n, 1)))
+        info = {k: getattr(st, k) for k, _ in _lib.TeeflowStats._fields_ if k != "reserved"}
+        return buf[:n, :st.n_levels].copy(), info
 
     def level_sizes(self, H: int, W: int):
         hs = (C.c_int32 * _lib.TEEFLOW_MAX_LEVELS)()

@@ -44,6 +44,6 @@ for rep in range(3):
     d32, d16 = eng.calc_clip(frd, want_f16=True)
     torch.cuda.synchronize(); dt = time.time() - t
     cnt, info = eng.last_counters()
-    print(f"device path rep{rep}: {dt*1e3:.1f} ms wall, device_ms {info['device_ms']:.1f}, launches {info['launches']}, {(N-1)/dt:.1f} pairs/s")
+    print(f"device path rep{rep}: {dt*1e3:.1f} ms wall, device_ms {info['device_ms']:.1f}, launches {info['solver_launches']}, {(N-1)/dt:.1f} pairs/s")
 cmp("device vs host path", d32.cpu().numpy(), f32)
 print("f16 equal astype:", bool(np.array_equal(d16.cpu().numpy(), f32.astype(np.float16))))
