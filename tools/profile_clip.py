@@ -1,0 +1,17 @@
+"""Profiling driver: one 64-frame 600x800 clip through the device path, twice (first = warm-up)."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from tee_optical_flow_b200.engine import TVL1Engine
+from tee_optical_flow_b200.synth import make_clip
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+fr = torch.from_numpy(make_clip(seed=0, n_frames=n, H=600, W=800)).cuda()
+eng = TVL1Engine(device=0)
+for r in range(reps):
+    f32, f16 = eng.calc_clip(fr, want_f32=False, want_f16=True)
+    torch.cuda.synchronize()
+    c, info = eng.last_counters()
+    print(r, info, "pairs/s", (n - 1) / info["device_ms"] * 1e3, flush=True)
