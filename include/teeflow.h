@@ -132,6 +132,11 @@ TEEFLOW_API int teeflow_get_stats(teeflow_handle h, teeflow_stats* out);
 /* Pyramid geometry the handle would use for an H x W image: level sizes (finest first). Returns the level count. */
 TEEFLOW_API int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws);
 
+/* Diagnostics: compares the engine's shared-reciprocal exact division with IEEE division (__fdiv_rn) on n
+ * pseudo-random operand pairs (mode 0: dual-update operand ranges, 1: thresholding ranges, 2: all exponents) and
+ * returns the number of bit mismatches (must be 0). */
+TEEFLOW_API int teeflow_selftest_division(teeflow_handle h, int mode, int64_t n, uint64_t seed, int64_t* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

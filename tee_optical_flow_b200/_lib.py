@@ -54,6 +54,7 @@ SIGNATURES = {
     "teeflow_get_counters": (C.c_int, [C.c_void_p, _i32p, C.c_int]),
     "teeflow_get_stats": (C.c_int, [C.c_void_p, C.POINTER(TeeflowStats)]),
     "teeflow_level_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p, _i32p]),
+    "teeflow_selftest_division": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

@@ -214,6 +214,50 @@ int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws
 
 }  // extern "C"
 
+// ---- self test of the exact-division fast path (diagnostics entry point, used by the GPU tests)
+__global__ void selftest_division_kernel(unsigned long long n, unsigned long long seed, int mode,
+                                         unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        // splitmix64 -> two floats with controlled exponents
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+        const unsigned ma = (unsigned)z & 0x7FFFFFu, mb = (unsigned)(z >> 23) & 0x7FFFFFu;
+        const unsigned sa = (unsigned)(z >> 46) & 1u;
+        int ea, eb;
+        if (mode == 0) {          // dual update: b = 1 + taut*|grad u| in [1, 2^6), |a| in [2^-30, 2^8)
+            ea = 127 - 30 + (int)((z >> 47) % 38); eb = 127 + (int)((z >> 53) % 6);
+        } else if (mode == 1) {   // thresholding: b = grad in [2^-23, 2^24), |a| <= l_t * b
+            eb = 127 - 23 + (int)((z >> 53) % 47); ea = eb - 5 - (int)((z >> 47) % 40);
+        } else {                  // wide: everything the guard may let through or reject
+            ea = 1 + (int)((z >> 47) % 253); eb = 1 + (int)((z >> 55) % 253);
+        }
+        float a = __uint_as_float((sa << 31) | ((unsigned)ea << 23) | ma);
+        const float b = __uint_as_float(((unsigned)eb << 23) | mb);
+        if ((z >> 62) == 3ull && mode != 2) a = sa ? -0.0f : 0.0f;     // zero numerators are common
+        const float q = div_exact(a, b), w = __fdiv_rn(a, b);
+        bad += (__float_as_uint(q) != __float_as_uint(w));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" TEEFLOW_API int teeflow_selftest_division(teeflow_handle h, int mode, int64_t n, uint64_t seed,
+                                                     int64_t* mismatches) {
+    if (!h || !mismatches || n < 0 || mode < 0 || mode > 2) return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    unsigned long long* d = nullptr;
+    CU_TRY(h, cudaMalloc(&d, sizeof(*d)));
+    CU_TRY(h, cudaMemset(d, 0, sizeof(*d)));
+    selftest_division_kernel<<<h->num_sms * 8, 256>>>((unsigned long long)n, seed, mode, d);
+    unsigned long long out = 0;
+    cudaError_t e = cudaMemcpy(&out, d, sizeof(out), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, TEEFLOW_ERR_CUDA, "selftest failed: %s", cudaGetErrorString(e));
+    *mismatches = (int64_t)out;
+    return TEEFLOW_OK;
+}
+
 template <typename T>
 static cudaError_t regrow(T*& ptr, size_t count) {
     if (ptr) cudaFree(ptr);
@@ -282,7 +326,8 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     for (int l = 0; l < L; ++l) {
         LevelGeom& g = P.lv[l];
         g.H = Hs[l]; g.W = Ws[l];
-        g.tiles_x = (g.W + kTW - 1) / kTW; g.tiles_y = (g.H + kTH - 1) / kTH; g.ntiles = g.tiles_x * g.tiles_y;
+        g.in_sx = (g.W + kIW - 1) / kIW; g.in_items = g.in_sx * ((g.H + kIR - 1) / kIR);
+        g.pw_sx = (g.W + 31) / 32; g.pw_items = g.pw_sx * ((g.H + kPR - 1) / kPR);
         g.pyr_off = off;
         off += ((long long)g.H * g.W + 63) / 64 * 64;
         g.scaled_eps = (float)(h->p.epsilon * h->p.epsilon * (double)(g.H * g.W));
@@ -302,7 +347,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     P.out_scale = out_scale;
     P.frame_pyr_stride = off;
     P.slot_px = ((long long)H * W + 63) / 64 * 64;
-    P.max_tiles = P.lv[0].ntiles;
+    P.max_tiles = P.lv[0].in_items;
 
     int rc = ensure_workspace(h, (size_t)n_frames, (size_t)off, S, (size_t)P.slot_px, (size_t)P.max_tiles, (size_t)n_pairs);
     if (rc) return rc;

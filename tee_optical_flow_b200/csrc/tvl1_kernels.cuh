@@ -3,18 +3,23 @@
 //  * pyramid kernels (once per FRAME, not per pair): u8/f32 -> f32, resize x0.8, centred gradient + pack.
 //  * tvl1_step_kernel: one persistent launch = one "super-step" of the device-side scheduler.  Every slot
 //    (a frame pair in flight) is in some phase (level-init / warp / median / inner / final); the work of all
-//    slots is flattened into tile items, persistent CTAs grid-stride over them, and the CTA that finishes the
-//    last tile of a slot reduces the slot's error partials (fixed order, float64) and advances its state
-//    machine exactly like OpenCV's procOneScale control flow.  No host round trip per
-//    iteration, per-pair exact early exit, continuous refill of finished slots.
+//    slots is flattened into warp-sized strip items, persistent warps grid-stride over them, and the warp that
+//    finishes the last strip of a slot reduces the slot's error partials (fixed order, float64) and advances
+//    its state machine exactly like OpenCV's procOneScale control flow.  No host round trip
+//    per iteration, per-pair exact early exit, continuous refill of finished slots.
+//  * The inner iteration is a warp-autonomous register-rolling stencil: a warp owns 31 output columns (+1 halo
+//    column) and walks down 32 rows; vertical neighbours stay in registers, horizontal ones come by warp
+//    shuffle, loads run one row ahead.  No shared memory, no block barrier.
 #pragma once
 #include "tvl1_device.cuh"
 
 namespace teeflow {
 
-constexpr int kTW = 64;        // tile width  (pixels)
-constexpr int kTH = 16;        // tile height (pixels)
 constexpr int kThreads = 256;  // threads per CTA
+constexpr int kWarpsPerCta = kThreads / 32;
+constexpr int kIW = 31;        // inner strip: output columns per warp (lane 31 = right halo column)
+constexpr int kIR = 32;        // inner strip: rows per warp
+constexpr int kPR = 8;         // pointwise strip: rows per warp (32 columns)
 
 // ------------------------------------------------------------------------------------------------ pyramid
 // level 0: convertTo(CV_32F, 1) for u8, x255 for f32 (tvl1flow.cpp: I0mult / I1mult)
@@ -117,32 +122,39 @@ __device__ inline void start_pair(const EngineParams& P, Slot& s, int pair) {
     for (int l = 0; l < kMaxLevels; ++l) { s.cnt[l][0] = 0; s.cnt[l][1] = 0; s.cnt[l][2] = 0; }
 }
 
-__device__ __forceinline__ int tiles_of(const EngineParams& P, const Slot& s) {
-    return (s.phase == PH_IDLE || s.pair < 0) ? 0 : P.lv[s.level].ntiles;
+__device__ __forceinline__ int items_of(const EngineParams& P, int phase, int pair, int level) {
+    if (phase == PH_IDLE || pair < 0) return 0;
+    if (phase == PH_FINAL) return P.lv[0].pw_items;
+    return phase == PH_INNER ? P.lv[level].in_items : P.lv[level].pw_items;
 }
 
-// ------------------------------------------------------------------------------------------------ tile ops
-// PH_LEVEL_INIT
-__device__ __forceinline__ void op_level_init(const EngineParams& P, const Slot& st, int slot, int tx0, int ty0) {
-    const LevelGeom g = P.lv[st.level];
+// ------------------------------------------------------------------------------------------------ strip ops
+// PH_LEVEL_INIT: u = 0 (coarsest) or u = resize(u_coarse, INTER_LINEAR) * (1/scaleStep); p = 0
+__device__ __forceinline__ void op_level_init(const EngineParams& P, int level, int ucur, int slot, int strip, int lane) {
+    const LevelGeom& g = P.lv[level];
     const size_t base = (size_t)slot * P.slot_px;
-    const bool coarsest = (st.level == P.L - 1);
-    float2* Ud = P.U[coarsest ? 0 : (st.ucur ^ 1)] + base;
-    const float2* Us = P.U[st.ucur] + base;
+    const bool coarsest = (level == P.L - 1);
+    float2* Ud = P.U[coarsest ? 0 : (ucur ^ 1)] + base;
+    const float2* Us = P.U[ucur] + base;
     float2* PXd = P.PX[0] + base;
     float2* PYd = P.PY[0] + base;
-    const int cH = coarsest ? 0 : P.lv[st.level + 1].H, cW = coarsest ? 0 : P.lv[st.level + 1].W;
-    for (int i = threadIdx.x; i < kTW * kTH; i += kThreads) {
-        const int x = tx0 + (i % kTW), y = ty0 + (i / kTW);
-        if (x >= g.W || y >= g.H) continue;
+    const int x = (strip % g.pw_sx) * 32 + lane;
+    const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
+    if (x >= g.W) return;
+    int x0 = 0, x1 = 0; float a0 = 0.f, a1 = 0.f;
+    int cH = 0, cW = 0;
+    if (!coarsest) {
+        cH = P.lv[level + 1].H; cW = P.lv[level + 1].W;
+        lin_coeff_x(x, g.up_sx, cW, x0, x1, a0, a1);
+    }
+    for (int y = y0; y < y1; ++y) {
         const size_t q = (size_t)y * g.W + x;
         float2 u = make_float2(0.f, 0.f);
         if (!coarsest) {
-            int x0, x1, y0, y1; float a0, a1, b0, b1;
-            lin_coeff_x(x, g.up_sx, cW, x0, x1, a0, a1);
-            lin_coeff_y(y, g.up_sy, cH, y0, y1, b0, b1);
-            const float2 s00 = Us[(size_t)y0 * cW + x0], s01 = Us[(size_t)y0 * cW + x1];
-            const float2 s10 = Us[(size_t)y1 * cW + x0], s11 = Us[(size_t)y1 * cW + x1];
+            int ya, yb; float b0, b1;
+            lin_coeff_y(y, g.up_sy, cH, ya, yb, b0, b1);
+            const float2 s00 = Us[(size_t)ya * cW + x0], s01 = Us[(size_t)ya * cW + x1];
+            const float2 s10 = Us[(size_t)yb * cW + x0], s11 = Us[(size_t)yb * cW + x1];
             const float r0x = s00.x * a0 + s01.x * a1, r1x = s10.x * a0 + s11.x * a1;
             const float r0y = s00.y * a0 + s01.y * a1, r1y = s10.y * a0 + s11.y * a1;
             u.x = (r0x * b0 + r1x * b1) * P.up_mul;
@@ -155,40 +167,43 @@ __device__ __forceinline__ void op_level_init(const EngineParams& P, const Slot&
 }
 
 // PH_WARP: buildFlowMap + remap(I1, I1x, I1y; INTER_CUBIC) + calcGradRho
-__device__ __forceinline__ void op_warp(const EngineParams& P, const Slot& st, int slot, int tx0, int ty0,
-                                        const float4* s_cubic) {
-    const LevelGeom g = P.lv[st.level];
+__device__ __forceinline__ void op_warp(const EngineParams& P, int level, int ucur, int pair, int slot, int strip,
+                                        int lane, const float4* s_cubic) {
+    const LevelGeom& g = P.lv[level];
     const size_t base = (size_t)slot * P.slot_px;
-    const float2* U = P.U[st.ucur] + base;
+    const float2* U = P.U[ucur] + base;
     float4* COEF = P.COEF + base;
-    const int fa = P.pair_a[st.pair], fb = P.pair_b[st.pair];
+    const int fa = P.pair_a[pair], fb = P.pair_b[pair];
     const float* I0 = P.pyrI + (size_t)fa * P.frame_pyr_stride + g.pyr_off;
     const float4* G1 = P.pyrG + (size_t)fb * P.frame_pyr_stride + g.pyr_off;
-    for (int i = threadIdx.x; i < kTW * kTH; i += kThreads) {
-        const int x = tx0 + (i % kTW), y = ty0 + (i / kTW);
-        if (x >= g.W || y >= g.H) continue;
+    const int x = (strip % g.pw_sx) * 32 + lane;
+    const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
+    if (x >= g.W) return;
+    for (int y = y0; y < y1; ++y) {
         const size_t q = (size_t)y * g.W + x;
         const float2 u = U[q];
+        const float i0 = I0[q];
         const float mx = (float)x + u.x, my = (float)y + u.y;
         const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic);
         const float Ix2 = w.y * w.y, Iy2 = w.z * w.z;
         float4 c;
         c.x = w.y; c.y = w.z;
         c.z = Ix2 + Iy2;
-        c.w = (w.x - w.y * u.x - w.z * u.y - I0[q]);
+        c.w = (w.x - w.y * u.x - w.z * u.y - i0);
         COEF[q] = c;
     }
 }
 
 // PH_MEDIAN: medianBlur(u1, ksize), medianBlur(u2, ksize) with BORDER_REPLICATE
-__device__ __forceinline__ void op_median(const EngineParams& P, const Slot& st, int slot, int tx0, int ty0) {
-    const LevelGeom g = P.lv[st.level];
+__device__ __forceinline__ void op_median(const EngineParams& P, int level, int ucur, int slot, int strip, int lane) {
+    const LevelGeom& g = P.lv[level];
     const size_t base = (size_t)slot * P.slot_px;
-    const float2* Us = P.U[st.ucur] + base;
-    float2* Ud = P.U[st.ucur ^ 1] + base;
-    for (int i = threadIdx.x; i < kTW * kTH; i += kThreads) {
-        const int x = tx0 + (i % kTW), y = ty0 + (i / kTW);
-        if (x >= g.W || y >= g.H) continue;
+    const float2* __restrict__ Us = P.U[ucur] + base;
+    float2* __restrict__ Ud = P.U[ucur ^ 1] + base;
+    const int x = (strip % g.pw_sx) * 32 + lane;
+    const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
+    if (x >= g.W) return;
+    for (int y = y0; y < y1; ++y) {
         float2 out;
         if (P.median == 5) {
             float v[25], w[25];
@@ -198,7 +213,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, const Slot& st,
 #pragma unroll
                 for (int dx = -2; dx <= 2; ++dx) {
                     const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = Us[(size_t)yy * g.W + xx];
+                    const float2 t = __ldg(Us + (size_t)yy * g.W + xx);
                     v[(dy + 2) * 5 + dx + 2] = t.x;
                     w[(dy + 2) * 5 + dx + 2] = t.y;
                 }
@@ -213,7 +228,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, const Slot& st,
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = Us[(size_t)yy * g.W + xx];
+                    const float2 t = __ldg(Us + (size_t)yy * g.W + xx);
                     v[(dy + 1) * 3 + dx + 1] = t.x;
                     w[(dy + 1) * 3 + dx + 1] = t.y;
                 }
@@ -225,92 +240,133 @@ __device__ __forceinline__ void op_median(const EngineParams& P, const Slot& st,
     }
 }
 
-// PH_INNER: one primal-dual iteration (estimateV, divergence, estimateU, forwardGradient, estimateDualVariables)
-// fused in one pass.  u_new is needed at (x,y), (x+1,y), (x,y+1) for the dual update, so it is computed on the tile
-// plus a one-pixel right/bottom halo into shared memory; p_old is read with a one-pixel left/top halo.
-__device__ __forceinline__ double op_inner(const EngineParams& P, const Slot& st, int slot, int tx0, int ty0,
-                                           float2* s_un) {
-    const LevelGeom g = P.lv[st.level];
+// ---- inner iteration pieces -------------------------------------------------------------------------------
+struct InnerRow { float2 u; float4 c; float2 px, py, pxl; };
+
+__device__ __forceinline__ InnerRow load_inner_row(const float2* __restrict__ U, const float4* __restrict__ COEF,
+                                                   const float2* __restrict__ PX, const float2* __restrict__ PY,
+                                                   size_t q, bool lane0_has_left) {
+    InnerRow r;
+    r.u = __ldg(U + q);
+    r.c = __ldg(COEF + q);
+    r.px = __ldg(PX + q);
+    r.py = __ldg(PY + q);
+    r.pxl = make_float2(0.f, 0.f);
+    if (lane0_has_left) r.pxl = __ldg(PX + q - 1);   // only lane 0 of a strip that does not start at x = 0
+    return r;
+}
+
+// estimateV + divergence + estimateU for one pixel (tvl1flow.cpp order of operations)
+__device__ __forceinline__ float2 estimate_u_px(const InnerRow& r, float2 pxl, float2 pyu, bool x_is_0, bool y_is_0,
+                                                float l_t, float theta) {
+    const float4 c = r.c;
+    const float rho = c.w + (c.x * r.u.x + c.y * r.u.y);
+    const float lg = l_t * c.z;
+    float d1 = 0.f, d2 = 0.f;
+    if (rho < -lg) { d1 = l_t * c.x; d2 = l_t * c.y; }
+    else if (rho > lg) { d1 = -l_t * c.x; d2 = -l_t * c.y; }
+    else if (c.z > FLT_EPSILON) { const float fi = div_exact(-rho, c.z); d1 = fi * c.x; d2 = fi * c.y; }
+    const float v1 = r.u.x + d1, v2 = r.u.y + d2;
+    float div1, div2;
+    if (x_is_0 && !y_is_0) {          // first column: v1 + v2 - v2(y-1)
+        div1 = r.px.x + r.py.x - pyu.x;
+        div2 = r.px.y + r.py.y - pyu.y;
+    } else {                          // interior; first row / corner follow with the missing terms == 0
+        div1 = (r.px.x - pxl.x) + (r.py.x - pyu.x);
+        div2 = (r.px.y - pxl.y) + (r.py.y - pyu.y);
+    }
+    return make_float2(v1 + theta * div1, v2 + theta * div2);
+}
+
+__device__ __forceinline__ float hypot_f(float a, float b) {
+    // static_cast<float>(hypot(a, b)) == (float)sqrt((double)a*a + (double)b*b)
+    if (a == 0.f && b == 0.f) return 0.f;
+    return (float)sqrt((double)a * (double)a + (double)b * (double)b);
+}
+
+// PH_INNER: one primal-dual iteration, warp-autonomous register-rolling strip
+__device__ __forceinline__ double op_inner(const EngineParams& P, int level, int ucur, int pcur, int slot, int strip,
+                                           int lane) {
+    const LevelGeom& g = P.lv[level];
+    const int W = g.W, H = g.H;
     const size_t base = (size_t)slot * P.slot_px;
-    const float2* __restrict__ U = P.U[st.ucur] + base;
-    float2* __restrict__ Un = P.U[st.ucur ^ 1] + base;
-    const float2* __restrict__ PX = P.PX[st.pcur] + base;
-    const float2* __restrict__ PY = P.PY[st.pcur] + base;
-    float2* __restrict__ PXn = P.PX[st.pcur ^ 1] + base;
-    float2* __restrict__ PYn = P.PY[st.pcur ^ 1] + base;
+    const float2* __restrict__ U = P.U[ucur] + base;
+    float2* __restrict__ Un = P.U[ucur ^ 1] + base;
+    const float2* __restrict__ PX = P.PX[pcur] + base;
+    const float2* __restrict__ PY = P.PY[pcur] + base;
+    float2* __restrict__ PXn = P.PX[pcur ^ 1] + base;
+    float2* __restrict__ PYn = P.PY[pcur ^ 1] + base;
     const float4* __restrict__ COEF = P.COEF + base;
     const float l_t = P.l_t, theta = P.theta, taut = P.taut;
-    constexpr int RW = kTW + 1, RH = kTH + 1;
+
+    const int x0 = (strip % g.in_sx) * kIW;
+    const int y0 = (strip / g.in_sx) * kIR, y1 = min(y0 + kIR, H);
+    const int x = x0 + lane;
+    const bool valid = x < W;                    // lane computes u_new
+    const bool owner = valid && lane < kIW;      // lane owns the outputs of its column
+    const bool has_right = x + 1 < W;
+    const bool x_is_0 = (x == 0);
+    const bool lane0_left = (lane == 0 && x0 > 0);
+    const int xc = valid ? x : W - 1;            // clamp: idle lanes read a legal address
+    size_t q = (size_t)y0 * W + xc;
+
     double err = 0.0;
-    // phase 1: u_new on the extended region
-    for (int i = threadIdx.x; i < RW * RH; i += kThreads) {
-        const int lx = i % RW, ly = i / RW;
-        const int x = tx0 + lx, y = ty0 + ly;
-        if (x >= g.W || y >= g.H) continue;
-        const size_t q = (size_t)y * g.W + x;
-        const float2 u = U[q];
-        const float4 c = COEF[q];
-        // estimateV
-        const float rho = c.w + (c.x * u.x + c.y * u.y);
-        float d1 = 0.f, d2 = 0.f;
-        if (rho < -l_t * c.z) { d1 = l_t * c.x; d2 = l_t * c.y; }
-        else if (rho > l_t * c.z) { d1 = -l_t * c.x; d2 = -l_t * c.y; }
-        else if (c.z > FLT_EPSILON) { const float fi = -rho / c.z; d1 = fi * c.x; d2 = fi * c.y; }
-        const float v1 = u.x + d1, v2 = u.y + d2;
-        // divergence of (p11,p12) and (p21,p22), backward differences
-        const float2 px = PX[q], py = PY[q];
-        float div1, div2;
-        if (x > 0 && y > 0) {
-            const float2 pxl = PX[q - 1], pyu = PY[q - g.W];
-            div1 = (px.x - pxl.x) + (py.x - pyu.x);
-            div2 = (px.y - pxl.y) + (py.y - pyu.y);
-        } else if (y == 0 && x > 0) {
-            const float2 pxl = PX[q - 1];
-            div1 = px.x - pxl.x + py.x;
-            div2 = px.y - pxl.y + py.y;
-        } else if (x == 0 && y > 0) {
-            const float2 pyu = PY[q - g.W];
-            div1 = px.x + py.x - pyu.x;
-            div2 = px.y + py.y - pyu.y;
-        } else {
-            div1 = px.x + py.x;
-            div2 = px.y + py.y;
-        }
-        // estimateU
-        float2 un;
-        un.x = v1 + theta * div1;
-        un.y = v2 + theta * div2;
-        s_un[ly * RW + lx] = un;
-        if (lx < kTW && ly < kTH) {
-            Un[q] = un;
-            const float t = (un.x - u.x) * (un.x - u.x) + (un.y - u.y) * (un.y - u.y);
-            err += (double)t;
-        }
+    float2 pyu = make_float2(0.f, 0.f);
+    if (y0 > 0) pyu = __ldg(PY + q - W);
+    InnerRow cur = load_inner_row(U, COEF, PX, PY, q, lane0_left);
+    InnerRow nxt = cur;
+    if (y0 + 1 < H) nxt = load_inner_row(U, COEF, PX, PY, q + W, lane0_left);
+
+    float2 pxl = make_float2(__shfl_up_sync(0xffffffffu, cur.px.x, 1), __shfl_up_sync(0xffffffffu, cur.px.y, 1));
+    if (lane == 0) pxl = cur.pxl;
+    float2 un = estimate_u_px(cur, pxl, pyu, x_is_0, y0 == 0, l_t, theta);
+    if (owner) {
+        Un[q] = un;
+        const float t = (un.x - cur.u.x) * (un.x - cur.u.x) + (un.y - cur.u.y) * (un.y - cur.u.y);
+        err += (double)t;
     }
-    __syncthreads();
-    // phase 2: forwardGradient(u_new) + estimateDualVariables
-    for (int i = threadIdx.x; i < kTW * kTH; i += kThreads) {
-        const int lx = i % kTW, ly = i / kTW;
-        const int x = tx0 + lx, y = ty0 + ly;
-        if (x >= g.W || y >= g.H) continue;
-        const size_t q = (size_t)y * g.W + x;
-        const float2 un = s_un[ly * RW + lx];
-        float u1x = 0.f, u2x = 0.f, u1y = 0.f, u2y = 0.f;
-        if (x < g.W - 1) { const float2 r = s_un[ly * RW + lx + 1]; u1x = r.x - un.x; u2x = r.y - un.y; }
-        if (y < g.H - 1) { const float2 b = s_un[(ly + 1) * RW + lx]; u1y = b.x - un.x; u2y = b.y - un.y; }
-        const float g1 = (float)sqrt((double)u1x * (double)u1x + (double)u1y * (double)u1y);
-        const float g2 = (float)sqrt((double)u2x * (double)u2x + (double)u2y * (double)u2y);
-        const float ng1 = 1.0f + taut * g1;
-        const float ng2 = 1.0f + taut * g2;
-        const float2 px = PX[q], py = PY[q];
+    float2 px_c = cur.px, py_c = cur.py;
+
+    for (int y = y0; y < y1; ++y) {
+        const bool has_next = (y + 1 < H);       // warp-uniform
+        float2 un_n = make_float2(0.f, 0.f);
+        InnerRow row = nxt;                      // row y+1 (already in flight)
+        if (y + 2 < H && y + 1 < y1) nxt = load_inner_row(U, COEF, PX, PY, q + 2 * (size_t)W, lane0_left);
+        if (has_next) {
+            float2 pl = make_float2(__shfl_up_sync(0xffffffffu, row.px.x, 1), __shfl_up_sync(0xffffffffu, row.px.y, 1));
+            if (lane == 0) pl = row.pxl;
+            un_n = estimate_u_px(row, pl, py_c, x_is_0, false, l_t, theta);
+            if (owner && y + 1 < y1) {
+                Un[q + W] = un_n;
+                const float t = (un_n.x - row.u.x) * (un_n.x - row.u.x) + (un_n.y - row.u.y) * (un_n.y - row.u.y);
+                err += (double)t;
+            }
+        }
+        // forwardGradient(u_new) + estimateDualVariables for row y
+        const float unr_x = __shfl_down_sync(0xffffffffu, un.x, 1), unr_y = __shfl_down_sync(0xffffffffu, un.y, 1);
+        const float u1x = has_right ? unr_x - un.x : 0.f, u2x = has_right ? unr_y - un.y : 0.f;
+        const float u1y = has_next ? un_n.x - un.x : 0.f, u2y = has_next ? un_n.y - un.y : 0.f;
+        const float g1 = hypot_f(u1x, u1y), g2 = hypot_f(u2x, u2y);
+        const float ng1 = 1.0f + taut * g1, ng2 = 1.0f + taut * g2;
+        const float a11 = px_c.x + taut * u1x, a12 = py_c.x + taut * u1y;
+        const float a21 = px_c.y + taut * u2x, a22 = py_c.y + taut * u2y;
         float2 pxn, pyn;
-        pxn.x = (px.x + taut * u1x) / ng1;   // p11
-        pyn.x = (py.x + taut * u1y) / ng1;   // p12
-        pxn.y = (px.y + taut * u2x) / ng2;   // p21
-        pyn.y = (py.y + taut * u2y) / ng2;   // p22
-        PXn[q] = pxn;
-        PYn[q] = pyn;
+        if (div_den_ok(ng1) && div_den_ok(ng2) && div_fast_ok(a11) && div_fast_ok(a12) && div_fast_ok(a21) &&
+            div_fast_ok(a22)) {
+            const float r1 = refined_rcp(ng1), r2 = refined_rcp(ng2);
+            pxn.x = div_with_rcp(a11, ng1, r1); pyn.x = div_with_rcp(a12, ng1, r1);
+            pxn.y = div_with_rcp(a21, ng2, r2); pyn.y = div_with_rcp(a22, ng2, r2);
+        } else {
+            pxn.x = __fdiv_rn(a11, ng1); pyn.x = __fdiv_rn(a12, ng1);
+            pxn.y = __fdiv_rn(a21, ng2); pyn.y = __fdiv_rn(a22, ng2);
+        }
+        if (owner) { PXn[q] = pxn; PYn[q] = pyn; }
+        un = un_n; px_c = row.px; py_c = row.py;
+        q += W;
     }
+    // fixed-order warp reduction of the float64 error partial
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err += __shfl_down_sync(0xffffffffu, err, o);
     return err;
 }
 
@@ -321,15 +377,16 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 
 // PH_FINAL: merge(u1,u2) * conversion_factor -> (H,W,2) f32 and/or f16 (calculate_optical_flow.py:600,403)
-__device__ __forceinline__ void op_final(const EngineParams& P, const Slot& st, int slot, int tx0, int ty0) {
-    const LevelGeom g = P.lv[0];
+__device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pair, int slot, int strip, int lane) {
+    const LevelGeom& g = P.lv[0];
     const size_t base = (size_t)slot * P.slot_px;
-    const float2* U = P.U[st.ucur] + base;
+    const float2* U = P.U[ucur] + base;
     const size_t npx = (size_t)g.H * g.W;
-    const int o0 = P.out_index[st.pair], o1 = P.dup_index[st.pair];
-    for (int i = threadIdx.x; i < kTW * kTH; i += kThreads) {
-        const int x = tx0 + (i % kTW), y = ty0 + (i / kTW);
-        if (x >= g.W || y >= g.H) continue;
+    const int o0 = P.out_index[pair], o1 = P.dup_index[pair];
+    const int x = (strip % g.pw_sx) * 32 + lane;
+    const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
+    if (x >= g.W) return;
+    for (int y = y0; y < y1; ++y) {
         const size_t q = (size_t)y * g.W + x;
         float2 u = U[q];
         u.x = u.x * P.out_scale;
@@ -347,20 +404,17 @@ __device__ __forceinline__ void op_final(const EngineParams& P, const Slot& st, 
 }
 
 // ------------------------------------------------------------------------------------------- the super-step
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     __shared__ int s_prefix[kMaxSlots + 1];
     __shared__ float4 s_cubic[32];
-    __shared__ float2 s_un[(kTW + 1) * (kTH + 1)];
-    __shared__ double s_red[kThreads / 32];
-    __shared__ int s_last;
 
     const Slot* __restrict__ cur = P.slots[parity];
     Slot* __restrict__ nxt = P.slots[parity ^ 1];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     if (tid < 32) s_cubic[tid] = cubic_coeffs(tid);
-    for (int s = tid; s < P.S; s += kThreads) s_prefix[s + 1] = tiles_of(P, cur[s]);
+    for (int s = tid; s < P.S; s += kThreads) s_prefix[s + 1] = items_of(P, cur[s].phase, cur[s].pair, cur[s].level);
     __syncthreads();
     if (tid == 0) {
         s_prefix[0] = 0;
@@ -374,61 +428,46 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
         for (int s = tid; s < P.S; s += kThreads)
             if (s_prefix[s + 1] == s_prefix[s]) nxt[s] = cur[s];
 
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        // slot of this item: largest s with prefix[s] <= item  (uniform across the CTA)
+    const int n_warps = gridDim.x * kWarpsPerCta;
+    // CTA-interleaved item order: the 8 warps of a CTA take 8 consecutive strips (shared cache lines)
+    for (int item = blockIdx.x * kWarpsPerCta + (tid >> 5); item < total; item += n_warps) {
         int lo = 0, hi = P.S;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] <= item) lo = mid; else hi = mid; }
         const int slot = lo;
-        const int tile = item - s_prefix[slot];
+        const int strip = item - s_prefix[slot];
         const Slot* sp = cur + slot;
-        Slot st;
-        st.pair = sp->pair; st.phase = sp->phase; st.level = sp->level; st.ucur = sp->ucur; st.pcur = sp->pcur;
-        const LevelGeom& g = P.lv[st.level];
-        const int tx0 = (tile % g.tiles_x) * kTW, ty0 = (tile / g.tiles_x) * kTH;
+        const int pair = sp->pair, phase = sp->phase, level = sp->level, ucur = sp->ucur, pcur = sp->pcur;
+        const int n_items = s_prefix[slot + 1] - s_prefix[slot];
 
         double err = 0.0;
-        switch (st.phase) {
-            case PH_LEVEL_INIT: op_level_init(P, st, slot, tx0, ty0); break;
-            case PH_WARP: op_warp(P, st, slot, tx0, ty0, s_cubic); break;
-            case PH_MEDIAN: op_median(P, st, slot, tx0, ty0); break;
-            case PH_INNER: err = op_inner(P, st, slot, tx0, ty0, s_un); break;
-            case PH_FINAL: op_final(P, st, slot, tx0, ty0); break;
+        switch (phase) {
+            case PH_LEVEL_INIT: op_level_init(P, level, ucur, slot, strip, lane); break;
+            case PH_WARP: op_warp(P, level, ucur, pair, slot, strip, lane, s_cubic); break;
+            case PH_MEDIAN: op_median(P, level, ucur, slot, strip, lane); break;
+            case PH_INNER: err = op_inner(P, level, ucur, pcur, slot, strip, lane); break;
+            case PH_FINAL: op_final(P, ucur, pair, slot, strip, lane); break;
             default: break;
         }
-
-        if (st.phase == PH_INNER) {
-            // deterministic CTA reduction of the float64 error partial (fixed shuffle tree, fixed warp order)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) err += __shfl_down_sync(0xffffffffu, err, o);
-            if ((tid & 31) == 0) s_red[tid >> 5] = err;
-        }
-        __syncthreads();   // all tile work of this CTA is issued; s_red complete
-        if (tid == 0) {
-            if (st.phase == PH_INNER) {
-                double e = 0.0;
-                for (int w = 0; w < kThreads / 32; ++w) e += s_red[w];
-                P.partial[(size_t)slot * P.max_tiles + tile] = e;
-            }
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+            if (phase == PH_INNER) P.partial[(size_t)slot * P.max_tiles + strip] = err;
             __threadfence();
             const unsigned ticket = atomicAdd(P.arrive + slot, 1u);
-            s_last = (ticket == (unsigned)g.ntiles - 1u);
+            last = (ticket == (unsigned)n_items - 1u);
         }
-        __syncthreads();
-        if (s_last) {
-            // last tile of this slot for this step: reduce the partials in tile order and advance the slot
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+            // last strip of this slot for this step: reduce the partials in strip order and advance the slot
             __threadfence();
             double e = 0.0;
-            if (st.phase == PH_INNER) {
+            if (phase == PH_INNER) {
                 const double* part = P.partial + (size_t)slot * P.max_tiles;
-                for (int t = tid; t < g.ntiles; t += kThreads) e += __ldcg(part + t);
+                for (int t = lane; t < n_items; t += 32) e += __ldcg(part + t);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-                if ((tid & 31) == 0) s_red[tid >> 5] = e;
-                __syncthreads();
-                e = 0.0;
-                if (tid == 0) for (int w = 0; w < kThreads / 32; ++w) e += s_red[w];
             }
-            if (tid == 0) {
+            if (lane == 0) {
                 Slot n = *sp;
                 if (n.phase == PH_FINAL) {
                     int* co = P.counters_out + (size_t)n.pair * kMaxLevels * 3;
@@ -445,7 +484,6 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
                 P.arrive[slot] = 0u;
             }
         }
-        __syncthreads();   // s_last / s_red / s_un are reused by the next item
     }
 }
 

@@ -219,3 +219,12 @@ def test_full_size_clip_properties(engine):
     fwd = f32[0]
     m = np.abs(fwd).sum(-1) > 0.05
     assert np.abs(rev.cpu().numpy()[0][m] + fwd[m]).mean() < 0.1
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_exact_division_matches_ieee(engine, mode):
+    """the shared-reciprocal division of the inner iteration is bit-identical to IEEE division (2^32 pairs)"""
+    import ctypes as C
+    bad = C.c_int64(-1)
+    rc = engine._lib.teeflow_selftest_division(engine._h, mode, 1 << 32, 1234 + mode, C.byref(bad))
+    assert rc == 0 and bad.value == 0
