@@ -7,8 +7,11 @@ from pathlib import Path
 
 from .exceptions import EngineUnavailableError
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libteeflow.so"
+# TEEFLOW_LIB: alternative build of the same library (kernel tuning experiments); default = the in-tree build
+LIB_PATH = Path(os.environ.get("TEEFLOW_LIB", PKG / "libteeflow.so"))
 
 TEEFLOW_MAX_LEVELS = 16
 TEEFLOW_U8, TEEFLOW_F32 = 0, 1

@@ -148,13 +148,13 @@ __device__ __forceinline__ void op_level_init(const EngineParams& P, int level, 
         lin_coeff_x(x, g.up_sx, cW, x0, x1, a0, a1);
     }
     for (int y = y0; y < y1; ++y) {
-        const size_t q = (size_t)y * g.W + x;
+        const unsigned q = (unsigned)(y * g.W + x);
         float2 u = make_float2(0.f, 0.f);
         if (!coarsest) {
             int ya, yb; float b0, b1;
             lin_coeff_y(y, g.up_sy, cH, ya, yb, b0, b1);
-            const float2 s00 = Us[(size_t)ya * cW + x0], s01 = Us[(size_t)ya * cW + x1];
-            const float2 s10 = Us[(size_t)yb * cW + x0], s11 = Us[(size_t)yb * cW + x1];
+            const float2 s00 = Us[(unsigned)(ya * cW + x0)], s01 = Us[(unsigned)(ya * cW + x1)];
+            const float2 s10 = Us[(unsigned)(yb * cW + x0)], s11 = Us[(unsigned)(yb * cW + x1)];
             const float r0x = s00.x * a0 + s01.x * a1, r1x = s10.x * a0 + s11.x * a1;
             const float r0y = s00.y * a0 + s01.y * a1, r1y = s10.y * a0 + s11.y * a1;
             u.x = (r0x * b0 + r1x * b1) * P.up_mul;
@@ -180,7 +180,7 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
     for (int y = y0; y < y1; ++y) {
-        const size_t q = (size_t)y * g.W + x;
+        const unsigned q = (unsigned)(y * g.W + x);
         const float2 u = U[q];
         const float i0 = I0[q];
         const float mx = (float)x + u.x, my = (float)y + u.y;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
 #pragma unroll
                 for (int dx = -2; dx <= 2; ++dx) {
                     const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = __ldg(Us + (size_t)yy * g.W + xx);
+                    const float2 t = __ldg(Us + (unsigned)(yy * g.W + xx));
                     v[(dy + 2) * 5 + dx + 2] = t.x;
                     w[(dy + 2) * 5 + dx + 2] = t.y;
                 }
@@ -228,7 +228,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = __ldg(Us + (size_t)yy * g.W + xx);
+                    const float2 t = __ldg(Us + (unsigned)(yy * g.W + xx));
                     v[(dy + 1) * 3 + dx + 1] = t.x;
                     w[(dy + 1) * 3 + dx + 1] = t.y;
                 }
@@ -236,7 +236,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
             out.x = median9(v);
             out.y = median9(w);
         }
-        Ud[(size_t)y * g.W + x] = out;
+        Ud[(unsigned)(y * g.W + x)] = out;
     }
 }
 
@@ -245,7 +245,7 @@ struct InnerRow { float2 u; float4 c; float2 px, py, pxl; };
 
 __device__ __forceinline__ InnerRow load_inner_row(const float2* __restrict__ U, const float4* __restrict__ COEF,
                                                    const float2* __restrict__ PX, const float2* __restrict__ PY,
-                                                   size_t q, bool lane0_has_left) {
+                                                   unsigned q, bool lane0_has_left) {
     InnerRow r;
     r.u = __ldg(U + q);
     r.c = __ldg(COEF + q);
@@ -256,16 +256,22 @@ __device__ __forceinline__ InnerRow load_inner_row(const float2* __restrict__ U,
     return r;
 }
 
-// estimateV + divergence + estimateU for one pixel (tvl1flow.cpp order of operations)
+// estimateV + divergence + estimateU for one pixel (tvl1flow.cpp order of operations), branch-free: the
+// thresholding division runs on every lane through the shared fast path and is selected where it applies.
 __device__ __forceinline__ float2 estimate_u_px(const InnerRow& r, float2 pxl, float2 pyu, bool x_is_0, bool y_is_0,
                                                 float l_t, float theta) {
     const float4 c = r.c;
     const float rho = c.w + (c.x * r.u.x + c.y * r.u.y);
     const float lg = l_t * c.z;
-    float d1 = 0.f, d2 = 0.f;
-    if (rho < -lg) { d1 = l_t * c.x; d2 = l_t * c.y; }
-    else if (rho > lg) { d1 = -l_t * c.x; d2 = -l_t * c.y; }
-    else if (c.z > FLT_EPSILON) { const float fi = div_exact(-rho, c.z); d1 = fi * c.x; d2 = fi * c.y; }
+    const bool c1 = rho < -lg;
+    const bool c2 = !c1 && rho > lg;
+    const bool c3 = !c1 && !c2 && c.z > FLT_EPSILON;
+    const float nrho = -rho;
+    float fi = div_with_rcp(nrho, c.z, refined_rcp(c.z));
+    if (c3 && !(div_den_ok(c.z) && div_fast_ok(nrho))) fi = __fdiv_rn(nrho, c.z);   // rare: IEEE slow path
+    const float a1 = l_t * c.x, a2 = l_t * c.y;
+    const float d1 = c1 ? a1 : (c2 ? -a1 : (c3 ? fi * c.x : 0.f));
+    const float d2 = c1 ? a2 : (c2 ? -a2 : (c3 ? fi * c.y : 0.f));
     const float v1 = r.u.x + d1, v2 = r.u.y + d2;
     float div1, div2;
     if (x_is_0 && !y_is_0) {          // first column: v1 + v2 - v2(y-1)
@@ -308,7 +314,7 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     const bool x_is_0 = (x == 0);
     const bool lane0_left = (lane == 0 && x0 > 0);
     const int xc = valid ? x : W - 1;            // clamp: idle lanes read a legal address
-    size_t q = (size_t)y0 * W + xc;
+    unsigned q = (unsigned)(y0 * W + xc);   // pixel offset inside the slot plane (< 2^28)
 
     double err = 0.0;
     float2 pyu = make_float2(0.f, 0.f);
@@ -327,11 +333,12 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     }
     float2 px_c = cur.px, py_c = cur.py;
 
+#pragma unroll 2
     for (int y = y0; y < y1; ++y) {
         const bool has_next = (y + 1 < H);       // warp-uniform
         float2 un_n = make_float2(0.f, 0.f);
         InnerRow row = nxt;                      // row y+1 (already in flight)
-        if (y + 2 < H && y + 1 < y1) nxt = load_inner_row(U, COEF, PX, PY, q + 2 * (size_t)W, lane0_left);
+        if (y + 2 < H && y + 1 < y1) nxt = load_inner_row(U, COEF, PX, PY, q + 2u * (unsigned)W, lane0_left);
         if (has_next) {
             float2 pl = make_float2(__shfl_up_sync(0xffffffffu, row.px.x, 1), __shfl_up_sync(0xffffffffu, row.px.y, 1));
             if (lane == 0) pl = row.pxl;
@@ -351,8 +358,11 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         const float a11 = px_c.x + taut * u1x, a12 = py_c.x + taut * u1y;
         const float a21 = px_c.y + taut * u2x, a22 = py_c.y + taut * u2y;
         float2 pxn, pyn;
-        if (div_den_ok(ng1) && div_den_ok(ng2) && div_fast_ok(a11) && div_fast_ok(a12) && div_fast_ok(a21) &&
-            div_fast_ok(a22)) {
+        // one guard for the four numerators: every |a| is 0 or >= 2^-100, the largest <= 2^100; ng in [1, 2^40]
+        const float amax = fmaxf(fmaxf(fabsf(a11), fabsf(a12)), fmaxf(fabsf(a21), fabsf(a22)));
+        const bool tiny = (fabsf(a11) < 7.888609e-31f && a11 != 0.f) || (fabsf(a12) < 7.888609e-31f && a12 != 0.f) ||
+                          (fabsf(a21) < 7.888609e-31f && a21 != 0.f) || (fabsf(a22) < 7.888609e-31f && a22 != 0.f);
+        if (!tiny && amax <= 1.2676506e30f && fmaxf(ng1, ng2) <= 1.0995116e12f) {
             const float r1 = refined_rcp(ng1), r2 = refined_rcp(ng2);
             pxn.x = div_with_rcp(a11, ng1, r1); pyn.x = div_with_rcp(a12, ng1, r1);
             pxn.y = div_with_rcp(a21, ng2, r2); pyn.y = div_with_rcp(a22, ng2, r2);
@@ -387,7 +397,7 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
     for (int y = y0; y < y1; ++y) {
-        const size_t q = (size_t)y * g.W + x;
+        const unsigned q = (unsigned)(y * g.W + x);
         float2 u = U[q];
         u.x = u.x * P.out_scale;
         u.y = u.y * P.out_scale;
@@ -404,7 +414,7 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
 }
 
 // ------------------------------------------------------------------------------------------- the super-step
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     __shared__ int s_prefix[kMaxSlots + 1];
     __shared__ float4 s_cubic[32];
