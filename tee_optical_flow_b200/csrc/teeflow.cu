@@ -226,8 +226,8 @@ __global__ void selftest_division_kernel(unsigned long long n, unsigned long lon
         const unsigned ma = (unsigned)z & 0x7FFFFFu, mb = (unsigned)(z >> 23) & 0x7FFFFFu;
         const unsigned sa = (unsigned)(z >> 46) & 1u;
         int ea, eb;
-        if (mode == 0) {          // dual update: b = 1 + taut*|grad u| in [1, 2^6), |a| in [2^-30, 2^8)
-            ea = 127 - 30 + (int)((z >> 47) % 38); eb = 127 + (int)((z >> 53) % 6);
+        if (mode == 0) {          // dual update: b = 1 + taut*|grad u| in [1, 2^24), |a| in [2^-110, 2^110)
+            ea = 127 - 110 + (int)((z >> 47) % 220); eb = 127 + (int)((z >> 55) % 24);
         } else if (mode == 1) {   // thresholding: b = grad in [2^-23, 2^24), |a| <= l_t * b
             eb = 127 - 23 + (int)((z >> 53) % 47); ea = eb - 5 - (int)((z >> 47) % 40);
         } else {                  // wide: everything the guard may let through or reject
@@ -236,7 +236,13 @@ __global__ void selftest_division_kernel(unsigned long long n, unsigned long lon
         float a = __uint_as_float((sa << 31) | ((unsigned)ea << 23) | ma);
         const float b = __uint_as_float(((unsigned)eb << 23) | mb);
         if ((z >> 62) == 3ull && mode != 2) a = sa ? -0.0f : 0.0f;     // zero numerators are common
-        const float q = div_exact(a, b), w = __fdiv_rn(a, b);
+        float q;
+        if (mode == 0) {          // the dual update's guard + shared-reciprocal path
+            q = dual_ok(dual_num_tiny(a), fabsf(a), b) ? div_with_rcp(a, b, refined_rcp(b)) : __fdiv_rn(a, b);
+        } else {
+            q = div_exact(a, b);
+        }
+        const float w = __fdiv_rn(a, b);
         bad += (__float_as_uint(q) != __float_as_uint(w));
     }
     if (bad) atomicAdd(mismatches, bad);

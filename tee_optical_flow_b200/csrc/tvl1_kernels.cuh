@@ -358,11 +358,10 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         const float a11 = px_c.x + taut * u1x, a12 = py_c.x + taut * u1y;
         const float a21 = px_c.y + taut * u2x, a22 = py_c.y + taut * u2y;
         float2 pxn, pyn;
-        // one guard for the four numerators: every |a| is 0 or >= 2^-100, the largest <= 2^100; ng in [1, 2^40]
+        // one guard for the four numerators: every |a| is 0 or >= 2^-100, the largest <= 2^100; ng in [1, 2^20]
         const float amax = fmaxf(fmaxf(fabsf(a11), fabsf(a12)), fmaxf(fabsf(a21), fabsf(a22)));
-        const bool tiny = (fabsf(a11) < 7.888609e-31f && a11 != 0.f) || (fabsf(a12) < 7.888609e-31f && a12 != 0.f) ||
-                          (fabsf(a21) < 7.888609e-31f && a21 != 0.f) || (fabsf(a22) < 7.888609e-31f && a22 != 0.f);
-        if (!tiny && amax <= 1.2676506e30f && fmaxf(ng1, ng2) <= 1.0995116e12f) {
+        const bool tiny = dual_num_tiny(a11) || dual_num_tiny(a12) || dual_num_tiny(a21) || dual_num_tiny(a22);
+        if (dual_ok(tiny, amax, fmaxf(ng1, ng2))) {
             const float r1 = refined_rcp(ng1), r2 = refined_rcp(ng2);
             pxn.x = div_with_rcp(a11, ng1, r1); pyn.x = div_with_rcp(a12, ng1, r1);
             pxn.y = div_with_rcp(a21, ng2, r2); pyn.y = div_with_rcp(a22, ng2, r2);
