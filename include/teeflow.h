@@ -132,6 +132,45 @@ TEEFLOW_API int teeflow_get_stats(teeflow_handle h, teeflow_stats* out);
 /* Pyramid geometry the handle would use for an H x W image: level sizes (finest first). Returns the level count. */
 TEEFLOW_API int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws);
 
+/* ---- WASE background compensation (calculate_optical_flow.py:649-660).
+ * teeflow_wase_weights: w[y,x,c] = sum_n bkgd[n,y,x,c] from the (n_frames,H,W,2) bool mask `mask_dict['bkgd']`
+ * (device pointers).  teeflow_set_wase(h, w_dev, H, W): every following calc_* subtracts, per pair, the scalar
+ *   background = mean of the non-zero entries of flow * bkgd  ==  sum(w f [f != 0]) / sum(w [f != 0])
+ * before the out_scale multiplication; w_dev stays owned by the caller; NULL switches it off (bkgd_comp='none').
+ * teeflow_get_backgrounds returns the scalars of the last calc (one per pair). */
+TEEFLOW_API int teeflow_wase_weights(teeflow_handle h, const uint8_t* bkgd_dev, int n_frames, int H, int W,
+                                     float* w_dev, void* stream);
+TEEFLOW_API int teeflow_set_wase(teeflow_handle h, const float* w_dev, int H, int W);
+TEEFLOW_API int teeflow_get_backgrounds(teeflow_handle h, float* bg_host, int n_pairs_cap);
+
+/* ---- masked radial / longitudinal decomposition with per-frame reductions
+ * (optical_flow/analysis.py:89-327: radial_vecgrid, calculate_comp_magnitude, calc_bidirectional_hist,
+ *  calculate_3dhist; optical_flow/cardiac_cycle_detection.py:100-116: per-frame angle mode).
+ * Inputs: the stored flow (N,H,W,2) fp16 (device), the (N,H,W,2) bool mask of the analysed label (device) --
+ * masked_arr = flow.astype(f32) * mask -- and the per-frame AV centroids (row, col) float64 (host).  The first
+ * `nframes` frames are analysed.  Output arrays (host, caller-allocated, any may be NULL) hold one value per
+ * frame; a frame without non-zero entries yields NaN (the caller applies the reference's carry-forward rule). */
+typedef struct {
+    float* mag_hi;      /* [nframes] np.percentile(|v| != 0, perc_hi), float32 arithmetic like numpy */
+    float* ang_mode;    /* [nframes] scipy.stats.mode(np.round(angle, 2) != 0) */
+    double* rad_hi;     /* [nframes] np.percentile(radial != 0, perc_hi) */
+    double* rad_lo;     /* [nframes]                              perc_lo */
+    double* long_hi;    /* [nframes] longitudinal */
+    double* long_lo;
+    int64_t* counts;    /* [nframes][4] non-zero entries: magnitude, angle, radial, longitudinal */
+    float mag_min, mag_max, ang_min, ang_max;          /* np.min / np.max over the analysed arrays */
+    double rad_min, rad_max, long_min, long_max;
+} teeflow_analysis;
+
+TEEFLOW_API int teeflow_analyze_clip(teeflow_handle h, const void* flow_f16_dev, const uint8_t* mask_dev,
+                                     const double* centroids_host, int nframes, int H, int W, double perc_lo,
+                                     double perc_hi, teeflow_analysis* out, void* stream);
+/* np.histogram(non-zero entries, bins=nbins, range=(edges[0], edges[nbins])) per frame for one quantity of the
+ * last teeflow_analyze_clip: 0 magnitude, 1 angle (float32 edges), 2 radial, 3 longitudinal (float64 edges);
+ * edges = np.linspace(first, last, nbins + 1) computed by the caller.  freq_host: [nframes][nbins] int64. */
+TEEFLOW_API int teeflow_analysis_histogram(teeflow_handle h, int quantity, const void* edges_host, int nbins,
+                                           int64_t* freq_host, void* stream);
+
 /* Diagnostics: compares the engine's shared-reciprocal exact division with IEEE division (__fdiv_rn) on n
  * pseudo-random operand pairs (mode 0: dual-update operand ranges, 1: thresholding ranges, 2: all exponents) and
  * returns the number of bit mismatches (must be 0). */

@@ -35,6 +35,17 @@ class TeeflowStats(C.Structure):
     ]
 
 
+class TeeflowAnalysis(C.Structure):
+    _fields_ = [
+        ("mag_hi", C.POINTER(C.c_float)), ("ang_mode", C.POINTER(C.c_float)),
+        ("rad_hi", C.POINTER(C.c_double)), ("rad_lo", C.POINTER(C.c_double)),
+        ("long_hi", C.POINTER(C.c_double)), ("long_lo", C.POINTER(C.c_double)),
+        ("counts", C.POINTER(C.c_int64)),
+        ("mag_min", C.c_float), ("mag_max", C.c_float), ("ang_min", C.c_float), ("ang_max", C.c_float),
+        ("rad_min", C.c_double), ("rad_max", C.c_double), ("long_min", C.c_double), ("long_max", C.c_double),
+    ]
+
+
 # every symbol include/teeflow.h declares: name -> (restype, argtypes)
 _i32p = C.POINTER(C.c_int32)
 SIGNATURES = {
@@ -57,6 +68,13 @@ SIGNATURES = {
     "teeflow_get_counters": (C.c_int, [C.c_void_p, _i32p, C.c_int]),
     "teeflow_get_stats": (C.c_int, [C.c_void_p, C.POINTER(TeeflowStats)]),
     "teeflow_level_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p, _i32p]),
+    "teeflow_wase_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "teeflow_set_wase": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "teeflow_get_backgrounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
+    "teeflow_analyze_clip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.c_int,
+                                       C.c_int, C.c_double, C.c_double, C.POINTER(TeeflowAnalysis), C.c_void_p]),
+    "teeflow_analysis_histogram": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int64),
+                                             C.c_void_p]),
     "teeflow_selftest_division": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]),
 }
 

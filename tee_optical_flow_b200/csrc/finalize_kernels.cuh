@@ -1,0 +1,235 @@
+// finalize_kernels.cuh -- kernels around the solver: WASE weight map and the masked radial / longitudinal
+// decomposition with its per-frame reductions (reference: optical_flow/analysis.py:89-327,
+// cardiac_cycle_detection.py:100-116, calculate_optical_flow.py:649-652).
+//
+// Exactness: order statistics are found by radix select on order-preserving keys (no sorting library, no
+// approximation), the percentile interpolation and the histogram binning replay numpy's arithmetic, and
+// cartToPolar replays OpenCV's FMA polynomial (oracle/probe_polar_percentile.py pins all three).
+#pragma once
+#include <cuda_fp16.h>
+#include "tvl1_device.cuh"
+
+namespace teeflow {
+
+// ---------------------------------------------------------------------------------------------- WASE weights
+// w[y,x,c] = sum_n bkgd[n,y,x,c]  (calculate_optical_flow.py:650: mask_dict['bkgd'] holds ALL frames)
+__global__ void wase_weights_kernel(const uint8_t* __restrict__ bkgd, int n_frames, int n_elem /* H*W*2 */,
+                                    float* __restrict__ w) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_elem; i += gridDim.x * blockDim.x) {
+        int c = 0;
+        for (int n = 0; n < n_frames; ++n) c += bkgd[(size_t)n * n_elem + i] != 0;
+        w[i] = (float)c;
+    }
+}
+
+// ------------------------------------------------------------------------------------- order-preserving keys
+__device__ __forceinline__ unsigned f32_key(float v) {
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ unsigned long long f64_key(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+// cv::cartToPolar (radians) as built in OpenCV 4.x with FMA SIMD: magnitude sqrt(fma(x,x,y*y)); fastAtan2
+// polynomial in degrees evaluated with FMAs, then * (float)(pi/180)
+__device__ __forceinline__ void cart_to_polar(float x, float y, float& mag, float& ang) {
+    mag = __fsqrt_rn(__fmaf_rn(x, x, __fmul_rn(y, y)));
+    const float p1 = 0.9997878412794807f * 57.29577951308232f, p3 = -0.3258083974640975f * 57.29577951308232f;
+    const float p5 = 0.1555786518463281f * 57.29577951308232f, p7 = -0.04432655554792128f * 57.29577951308232f;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+    const float c = __fdiv_rn(mn, __fadd_rn(mx, 2.220446049250313e-16f));
+    const float cc = __fmul_rn(c, c);
+    float a = __fmaf_rn(p7, cc, p5);
+    a = __fmaf_rn(a, cc, p3);
+    a = __fmaf_rn(a, cc, p1);
+    a = __fmul_rn(a, c);
+    if (ay > ax) a = __fsub_rn(90.f, a);
+    if (x < 0.f) a = __fsub_rn(180.f, a);
+    if (y < 0.f) a = __fsub_rn(360.f, a);
+    ang = __fmul_rn(a, 0.017453292519943295f);
+}
+
+struct FrameStats {
+    unsigned long long cnt[4];       // non-zero counts: mag, ang, rad, long
+    unsigned mag_min, mag_max, ang_min, ang_max;          // keys over ALL pixels (np.min / np.max of the arrays)
+    unsigned long long rad_min, rad_max, long_min, long_max;
+};
+constexpr int kAngBins = 640;        // rint(ang * 100) in [0, 628]
+
+__global__ void analysis_init_kernel(FrameStats* st, unsigned* ang_hist, int nframes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nframes) {
+        FrameStats s;
+        for (int k = 0; k < 4; ++k) s.cnt[k] = 0;
+        s.mag_min = s.ang_min = 0xffffffffu; s.mag_max = s.ang_max = 0u;
+        s.rad_min = s.long_min = ~0ull; s.rad_max = s.long_max = 0ull;
+        st[i] = s;
+    }
+    for (int k = i; k < nframes * kAngBins; k += gridDim.x * blockDim.x) ang_hist[k] = 0u;
+}
+
+// masked_arr = vel_array * mask (optical_flow_dataset.py:189-197); mag/ang (analysis.py:232-236);
+// radial unit grid + projections in float64 (analysis.py:89-163).  grid = (chunks, nframes)
+__global__ void __launch_bounds__(256)
+analysis_values_kernel(const __half2* __restrict__ flow16, const uint8_t* __restrict__ mask,
+                       const double* __restrict__ centroids, int H, int W, float* __restrict__ mag_out,
+                       float* __restrict__ ang_out, double* __restrict__ rad_out, double* __restrict__ long_out,
+                       FrameStats* __restrict__ stats, unsigned* __restrict__ ang_hist) {
+    __shared__ unsigned s_hist[kAngBins];
+    __shared__ unsigned long long s_cnt[4];
+    __shared__ unsigned s_k32[4];
+    __shared__ unsigned long long s_k64[4];
+    const int f = blockIdx.y;
+    const int npx = H * W;
+    for (int k = threadIdx.x; k < kAngBins; k += blockDim.x) s_hist[k] = 0u;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) { s_k32[0] = 0xffffffffu; s_k32[1] = 0u; s_k32[2] = 0xffffffffu; s_k32[3] = 0u;
+                            s_k64[0] = ~0ull; s_k64[1] = 0ull; s_k64[2] = ~0ull; s_k64[3] = 0ull; }
+    __syncthreads();
+    const double cH = centroids[2 * f], cW = centroids[2 * f + 1];
+    const size_t fo = (size_t)f * npx;
+    unsigned c_mag = 0, c_ang = 0, c_rad = 0, c_long = 0;
+    unsigned mag_mn = 0xffffffffu, mag_mx = 0u, ang_mn = 0xffffffffu, ang_mx = 0u;
+    unsigned long long rad_mn = ~0ull, rad_mx = 0ull, long_mn = ~0ull, long_mx = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        const int r = i / W, c = i - r * W;
+        const float2 v = __half22float2(flow16[fo + i]);
+        const uchar2 m = reinterpret_cast<const uchar2*>(mask)[fo + i];
+        const float fx = v.x * (m.x ? 1.f : 0.f), fy = v.y * (m.y ? 1.f : 0.f);
+        float mg, an;
+        cart_to_polar(fx, fy, mg, an);
+        const double v0 = cH - (double)r, v1 = cW - (double)c;
+        const double nrm = sqrt(v0 * v0 + v1 * v1);
+        double u0 = v0 / nrm, u1 = v1 / nrm;
+        if (u0 != u0) u0 = 0.0;                 // np.nan_to_num(vec / norm, nan=0): 0/0 at the centroid
+        if (u1 != u1) u1 = 0.0;
+        const double rad = (double)fx * u0 + (double)fy * u1;
+        const double lng = (double)fx * u1 + (double)fy * (-u0);
+        mag_out[fo + i] = mg; ang_out[fo + i] = an; rad_out[fo + i] = rad; long_out[fo + i] = lng;
+        c_mag += mg != 0.f; c_rad += rad != 0.0; c_long += lng != 0.0;
+        if (an != 0.f) {
+            ++c_ang;
+            const int key = (int)rintf(__fmul_rn(an, 100.f));     // np.round(ang, 2) == rint(ang*100)/100
+            if (key != 0) atomicAdd(&s_hist[min(key, kAngBins - 1)], 1u);
+        }
+        const unsigned km = f32_key(mg), ka = f32_key(an);
+        mag_mn = min(mag_mn, km); mag_mx = max(mag_mx, km); ang_mn = min(ang_mn, ka); ang_mx = max(ang_mx, ka);
+        const unsigned long long kr = f64_key(rad), kl = f64_key(lng);
+        rad_mn = min(rad_mn, kr); rad_mx = max(rad_mx, kr); long_mn = min(long_mn, kl); long_mx = max(long_mx, kl);
+    }
+    atomicAdd(&s_cnt[0], (unsigned long long)c_mag); atomicAdd(&s_cnt[1], (unsigned long long)c_ang);
+    atomicAdd(&s_cnt[2], (unsigned long long)c_rad); atomicAdd(&s_cnt[3], (unsigned long long)c_long);
+    atomicMin(&s_k32[0], mag_mn); atomicMax(&s_k32[1], mag_mx); atomicMin(&s_k32[2], ang_mn); atomicMax(&s_k32[3], ang_mx);
+    atomicMin(&s_k64[0], rad_mn); atomicMax(&s_k64[1], rad_mx); atomicMin(&s_k64[2], long_mn); atomicMax(&s_k64[3], long_mx);
+    __syncthreads();
+    FrameStats* st = stats + f;
+    if (threadIdx.x < 4) atomicAdd(&st->cnt[threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        atomicMin(&st->mag_min, s_k32[0]); atomicMax(&st->mag_max, s_k32[1]);
+        atomicMin(&st->ang_min, s_k32[2]); atomicMax(&st->ang_max, s_k32[3]);
+        atomicMin(&st->rad_min, s_k64[0]); atomicMax(&st->rad_max, s_k64[1]);
+        atomicMin(&st->long_min, s_k64[2]); atomicMax(&st->long_max, s_k64[3]);
+    }
+    for (int k = threadIdx.x; k < kAngBins; k += blockDim.x)
+        if (s_hist[k]) atomicAdd(&ang_hist[(size_t)f * kAngBins + k], s_hist[k]);
+}
+
+// Exact order statistics of the NON-ZERO values of one frame by MSB-first radix select (8-bit digits).
+// One CTA per (frame, target group): quantity 0 = mag (float32), 1 = rad, 2 = long (float64); up to 4 target
+// ranks (0-based, among the non-zero values in ascending order; rank < 0 = unused).
+constexpr int kSelTargets = 4;
+__global__ void __launch_bounds__(1024)
+radix_select_kernel(const float* __restrict__ mag, const double* __restrict__ rad, const double* __restrict__ lng,
+                    int npx, const long long* __restrict__ ranks /* [nframes][3][4] */,
+                    unsigned long long* __restrict__ out_keys /* [nframes][3][4] */) {
+    __shared__ unsigned s_hist[kSelTargets][256];
+    __shared__ unsigned long long s_prefix[kSelTargets];
+    __shared__ long long s_rank[kSelTargets];
+    const int f = blockIdx.x, qn = blockIdx.y;
+    const bool is64 = qn != 0;
+    const int nbits = is64 ? 64 : 32;
+    const size_t fo = (size_t)f * npx;
+    const unsigned long long zero_pos = is64 ? 0x8000000000000000ull : 0x80000000ull;          // key of +0
+    const unsigned long long zero_neg = is64 ? 0x7fffffffffffffffull : 0x7fffffffull;          // key of -0
+    if (threadIdx.x < kSelTargets) {
+        s_prefix[threadIdx.x] = 0ull;
+        s_rank[threadIdx.x] = ranks[((size_t)f * 3 + qn) * kSelTargets + threadIdx.x];
+    }
+    __syncthreads();
+    for (int shift = nbits - 8; shift >= 0; shift -= 8) {
+        for (int k = threadIdx.x; k < kSelTargets * 256; k += blockDim.x) (&s_hist[0][0])[k] = 0u;
+        __syncthreads();
+        unsigned long long pre[kSelTargets];
+        bool act[kSelTargets];
+#pragma unroll
+        for (int t = 0; t < kSelTargets; ++t) { pre[t] = s_prefix[t]; act[t] = s_rank[t] >= 0; }
+        for (int i = threadIdx.x; i < npx; i += blockDim.x) {
+            unsigned long long key;
+            if (qn == 0) key = (unsigned long long)f32_key(mag[fo + i]);
+            else key = f64_key(qn == 1 ? rad[fo + i] : lng[fo + i]);
+            if (key == zero_pos || key == zero_neg) continue;       // flat[flat != 0]
+            const unsigned digit = (unsigned)(key >> shift) & 0xffu;
+            const unsigned long long hi = (shift + 8 >= 64) ? 0ull : (key >> (shift + 8));
+#pragma unroll
+            for (int t = 0; t < kSelTargets; ++t) {
+                const unsigned long long phi = (shift + 8 >= 64) ? 0ull : (pre[t] >> (shift + 8));
+                if (act[t] && hi == phi) atomicAdd(&s_hist[t][digit], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < kSelTargets && s_rank[threadIdx.x] >= 0) {
+            const int t = threadIdx.x;
+            long long r = s_rank[t];
+            int d = 0;
+            for (; d < 255; ++d) {
+                const long long c = (long long)s_hist[t][d];
+                if (r < c) break;
+                r -= c;
+            }
+            s_rank[t] = r;
+            s_prefix[t] |= ((unsigned long long)d) << shift;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < kSelTargets)
+        out_keys[((size_t)f * 3 + qn) * kSelTargets + threadIdx.x] = s_prefix[threadIdx.x];
+}
+
+// np.histogram(flat_nonzero, bins=nbins, range=(first, last)) with numpy's uniform-bin arithmetic
+// (lib/_histograms_impl.py): index = int(((v - first) / (last - first)) * nbins), fixed up against the edges.
+// T = float (mag, ang) or double (rad, long).  grid = (chunks, nframes)
+template <typename T>
+__global__ void __launch_bounds__(256)
+np_histogram_kernel(const T* __restrict__ vals, int npx, const T* __restrict__ edges, int nbins, T first, T last,
+                    unsigned long long* __restrict__ freq /* [nframes][nbins] */) {
+    extern __shared__ unsigned s_bins[];
+    const int f = blockIdx.y;
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x) s_bins[k] = 0u;
+    __syncthreads();
+    const T denom = last - first;
+    const size_t fo = (size_t)f * npx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        const T v = vals[fo + i];
+        if (v == (T)0 || !(v >= first) || !(v <= last)) continue;
+        const T fi = ((v - first) / denom) * (T)nbins;
+        int idx = (int)fi;
+        if (idx == nbins) idx -= 1;
+        if (v < edges[idx]) idx -= 1;
+        if (idx != nbins - 1 && v >= edges[idx + 1]) idx += 1;
+        atomicAdd(&s_bins[idx], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x)
+        if (s_bins[k]) atomicAdd(&freq[(size_t)f * nbins + k], (unsigned long long)s_bins[k]);
+}
+
+}  // namespace teeflow

@@ -15,6 +15,7 @@
 
 #include "../../include/teeflow.h"
 #include "tvl1_kernels.cuh"
+#include "finalize_kernels.cuh"
 
 using namespace teeflow;
 
@@ -42,6 +43,18 @@ struct teeflow_engine {
     int* ctl = nullptr;        // [0] next_pair, [1] pairs_done
     int* pair_lists = nullptr; // [4][cap_pairs]
     int* counters = nullptr;   // [cap_pairs][kMaxLevels][3]
+    float* bg = nullptr;       // [cap_pairs] WASE background scalars
+    const float* wase_w = nullptr;  // caller-owned [H][W][2] weight map (nullptr: no background compensation)
+    int wase_H = 0, wase_W = 0;
+    // analysis scratch (teeflow_analyze_clip)
+    size_t an_cap = 0; int an_frames = 0, an_H = 0, an_W = 0;
+    float *an_mag = nullptr, *an_ang = nullptr;
+    double *an_rad = nullptr, *an_long = nullptr, *an_cent = nullptr;
+    FrameStats* an_stats = nullptr;
+    unsigned* an_anghist = nullptr;
+    long long* an_ranks = nullptr;
+    unsigned long long* an_keys = nullptr;
+    void* an_edges = nullptr; unsigned long long* an_freq = nullptr; size_t an_freq_cap = 0;
     int* h_done = nullptr;     // pinned
     void* stage_in = nullptr; size_t stage_in_bytes = 0;
     void* stage_f32 = nullptr; size_t stage_f32_bytes = 0;
@@ -153,7 +166,10 @@ int teeflow_destroy(teeflow_handle h) {
     cudaFree(h->pyrI); cudaFree(h->pyrG);
     for (int i = 0; i < 2; ++i) { cudaFree(h->U[i]); cudaFree(h->PX[i]); cudaFree(h->PY[i]); }
     cudaFree(h->COEF); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
-    cudaFree(h->pair_lists); cudaFree(h->counters);
+    cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg);
+    cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
+    cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
+    cudaFree(h->an_edges); cudaFree(h->an_freq);
     cudaFree(h->stage_in); cudaFree(h->stage_f32); cudaFree(h->stage_f16);
     cudaFreeHost(h->h_done);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -298,6 +314,7 @@ static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_strid
     if (n_pairs > h->cap_pairs) {
         CU_TRY(h, regrow(h->pair_lists, 4 * n_pairs));
         CU_TRY(h, regrow(h->counters, n_pairs * kMaxLevels * 3));
+        CU_TRY(h, regrow(h->bg, n_pairs));
         h->cap_pairs = n_pairs;
     }
     return TEEFLOW_OK;
@@ -353,7 +370,9 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     P.out_scale = out_scale;
     P.frame_pyr_stride = off;
     P.slot_px = ((long long)H * W + 63) / 64 * 64;
-    P.max_tiles = P.lv[0].in_items;
+    P.max_tiles = std::max(P.lv[0].in_items, 2 * P.lv[0].pw_items);
+    if (h->wase_w && (h->wase_H != H || h->wase_W != W))
+        return fail(h, TEEFLOW_ERR_BAD_SHAPE, "WASE weight map is %dx%d but the frames are %dx%d", h->wase_H, h->wase_W, H, W);
 
     int rc = ensure_workspace(h, (size_t)n_frames, (size_t)off, S, (size_t)P.slot_px, (size_t)P.max_tiles, (size_t)n_pairs);
     if (rc) return rc;
@@ -364,10 +383,13 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     P.pair_a = h->pair_lists; P.pair_b = h->pair_lists + h->cap_pairs;
     P.out_index = h->pair_lists + 2 * h->cap_pairs; P.dup_index = h->pair_lists + 3 * h->cap_pairs;
     P.counters_out = h->counters;
+    P.wase_w = h->wase_w;
+    P.bg_out = h->bg;
     P.flow_f32 = (float2*)flow_f32_dev;
     P.flow_f16 = (uint32_t*)flow_f16_dev;
 
     CU_TRY(h, cudaEventRecord(h->ev_t0, stream));
+    CU_TRY(h, cudaMemsetAsync(h->bg, 0, sizeof(float) * n_pairs, stream));
     // pair lists (small) -- pageable host memory: the copies are staged by the runtime before the call returns
     CU_TRY(h, cudaMemcpyAsync((void*)P.pair_a, pair_a, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream));
     CU_TRY(h, cudaMemcpyAsync((void*)P.pair_b, pair_b, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream));
@@ -417,7 +439,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     const int grid = h->num_sms * h->ctas_per_sm;
     const int chunk = 16;
     // upper bound on steps per pair: per level 1 init + warps * (1 + outer * (1 + inner)), + 1 final
-    const long long steps_per_pair = (long long)L * (1 + (long long)h->p.warps * (1 + (long long)h->p.outer_iterations * (1 + h->p.inner_iterations))) + 1;
+    const long long steps_per_pair = (long long)L * (1 + (long long)h->p.warps * (1 + (long long)h->p.outer_iterations * (1 + h->p.inner_iterations))) + 2;
     const long long max_steps = steps_per_pair * ((n_pairs + S - 1) / S + 1) + 2 * chunk;
     long long step = 0;
     int pending = 0;  // chunks whose done-counter copy has been issued but not yet checked
@@ -553,6 +575,193 @@ int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap) {
 int teeflow_get_stats(teeflow_handle h, teeflow_stats* out) {
     if (!h || !out) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
     *out = h->st;
+    return TEEFLOW_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// ---- WASE background compensation (calculate_optical_flow.py:649-660)
+int teeflow_wase_weights(teeflow_handle h, const uint8_t* bkgd_dev, int n_frames, int H, int W, float* w_dev,
+                         void* stream) {
+    if (!h || !bkgd_dev || !w_dev || n_frames < 1 || H < 1 || W < 1) return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int n_elem = H * W * 2;
+    wase_weights_kernel<<<std::min((n_elem + 255) / 256, h->num_sms * 16), 256, 0, (cudaStream_t)stream>>>(
+        bkgd_dev, n_frames, n_elem, w_dev);
+    CU_TRY(h, cudaGetLastError());
+    return TEEFLOW_OK;
+}
+
+int teeflow_set_wase(teeflow_handle h, const float* w_dev, int H, int W) {
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (w_dev && (H < 1 || W < 1)) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "bad weight map shape");
+    h->wase_w = w_dev; h->wase_H = H; h->wase_W = W;
+    return TEEFLOW_OK;
+}
+
+int teeflow_get_backgrounds(teeflow_handle h, float* bg_host, int n_pairs_cap) {
+    if (!h || !bg_host) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
+    const int n = h->st.n_pairs;
+    if (n_pairs_cap < n) return fail(h, TEEFLOW_ERR_BAD_ARG, "buffer holds %d pairs, need %d", n_pairs_cap, n);
+    CU_TRY(h, cudaSetDevice(h->device));
+    if (n > 0) CU_TRY(h, cudaMemcpy(bg_host, h->bg, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+// ---- masked radial / longitudinal decomposition + per-frame reductions (analysis.py, cardiac_cycle_detection.py)
+static float pct_f32(const float a, const float b, int n, double q) {
+    // np.percentile on a float32 array: the whole computation runs in float32 (numpy >= 2)
+    if (n <= 1) return a;
+    const float qf = (float)q / 100.0f;
+    const float virt = (float)(n - 1) * qf;
+    const float g = virt - floorf(virt);
+    const float d = b - a;
+    return g >= 0.5f ? b - d * (1.0f - g) : a + d * g;
+}
+static double pct_f64(const double a, const double b, long long n, double q) {
+    if (n <= 1) return a;
+    const double virt = (double)(n - 1) * (q / 100.0);
+    const double g = virt - floor(virt);
+    const double d = b - a;
+    return g >= 0.5 ? b - d * (1.0 - g) : a + d * g;
+}
+static void pct_ranks(long long n, double q, bool f32, long long* lo, long long* hi) {
+    if (n <= 0) { *lo = *hi = -1; return; }
+    double prev;
+    if (f32) { const float virt = (float)(n - 1) * ((float)q / 100.0f); prev = floorf(virt); }
+    else { const double virt = (double)(n - 1) * (q / 100.0); prev = floor(virt); }
+    long long l = (long long)prev;
+    if (l >= n - 1) { *lo = *hi = n - 1; return; }   // numpy: index above bounds -> last element twice
+    if (l < 0) l = 0;
+    *lo = l; *hi = l + 1;
+}
+
+static float host_key_f32(unsigned long long k64) {
+    unsigned k = (unsigned)k64; unsigned b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k; float v; memcpy(&v, &b, 4); return v;
+}
+static double host_key_f64(unsigned long long k) {
+    unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k; double v; memcpy(&v, &b, 8); return v;
+}
+
+int teeflow_analyze_clip(teeflow_handle h, const void* flow_f16_dev, const uint8_t* mask_dev,
+                         const double* centroids_host, int nframes, int H, int W, double perc_lo, double perc_hi,
+                         teeflow_analysis* out, void* stream_v) {
+    if (!h || !flow_f16_dev || !mask_dev || !centroids_host || !out) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
+    if (nframes < 1 || H < 1 || W < 1) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "bad shape");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t npx = (size_t)H * W, need = npx * nframes;
+    if (need > h->an_cap) {
+        CU_TRY(h, regrow(h->an_mag, need)); CU_TRY(h, regrow(h->an_ang, need));
+        CU_TRY(h, regrow(h->an_rad, need)); CU_TRY(h, regrow(h->an_long, need));
+        h->an_cap = need;
+    }
+    if (nframes > h->an_frames || !h->an_stats) {
+        CU_TRY(h, regrow(h->an_stats, (size_t)nframes)); CU_TRY(h, regrow(h->an_anghist, (size_t)nframes * kAngBins));
+        CU_TRY(h, regrow(h->an_cent, (size_t)nframes * 2)); CU_TRY(h, regrow(h->an_ranks, (size_t)nframes * 12));
+        CU_TRY(h, regrow(h->an_keys, (size_t)nframes * 12));
+    }
+    h->an_frames = nframes; h->an_H = H; h->an_W = W;
+    CU_TRY(h, cudaMemcpyAsync(h->an_cent, centroids_host, sizeof(double) * 2 * nframes, cudaMemcpyHostToDevice, stream));
+    analysis_init_kernel<<<(nframes * kAngBins + 255) / 256, 256, 0, stream>>>(h->an_stats, h->an_anghist, nframes);
+    const int chunks = std::max(1, std::min((int)((npx + 256 * 8 - 1) / (256 * 8)), 64));
+    analysis_values_kernel<<<dim3(chunks, nframes), 256, 0, stream>>>(
+        (const __half2*)flow_f16_dev, mask_dev, h->an_cent, H, W, h->an_mag, h->an_ang, h->an_rad, h->an_long,
+        h->an_stats, h->an_anghist);
+    CU_TRY(h, cudaGetLastError());
+    std::vector<FrameStats> st(nframes);
+    std::vector<unsigned> ah((size_t)nframes * kAngBins);
+    CU_TRY(h, cudaMemcpyAsync(st.data(), h->an_stats, sizeof(FrameStats) * nframes, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(h, cudaMemcpyAsync(ah.data(), h->an_anghist, sizeof(unsigned) * ah.size(), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(h, cudaStreamSynchronize(stream));
+
+    // global ranges (np.min / np.max over the whole array, zeros included)
+    unsigned mmin = 0xffffffffu, mmax = 0, amin = 0xffffffffu, amax = 0;
+    unsigned long long rmin = ~0ull, rmax = 0, lmin = ~0ull, lmax = 0;
+    for (int f = 0; f < nframes; ++f) {
+        mmin = std::min(mmin, st[f].mag_min); mmax = std::max(mmax, st[f].mag_max);
+        amin = std::min(amin, st[f].ang_min); amax = std::max(amax, st[f].ang_max);
+        rmin = std::min(rmin, st[f].rad_min); rmax = std::max(rmax, st[f].rad_max);
+        lmin = std::min(lmin, st[f].long_min); lmax = std::max(lmax, st[f].long_max);
+    }
+    out->mag_min = host_key_f32(mmin); out->mag_max = host_key_f32(mmax);
+    out->ang_min = host_key_f32(amin); out->ang_max = host_key_f32(amax);
+    out->rad_min = host_key_f64(rmin); out->rad_max = host_key_f64(rmax);
+    out->long_min = host_key_f64(lmin); out->long_max = host_key_f64(lmax);
+
+    // target ranks per frame: [q][4] = mag: (hi.lo, hi.hi, -, -); rad/long: (lo.lo, lo.hi, hi.lo, hi.hi)
+    std::vector<long long> ranks((size_t)nframes * 12, -1);
+    for (int f = 0; f < nframes; ++f) {
+        long long* r = ranks.data() + (size_t)f * 12;
+        pct_ranks((long long)st[f].cnt[0], perc_hi, true, &r[0], &r[1]);
+        pct_ranks((long long)st[f].cnt[2], perc_lo, false, &r[4], &r[5]);
+        pct_ranks((long long)st[f].cnt[2], perc_hi, false, &r[6], &r[7]);
+        pct_ranks((long long)st[f].cnt[3], perc_lo, false, &r[8], &r[9]);
+        pct_ranks((long long)st[f].cnt[3], perc_hi, false, &r[10], &r[11]);
+    }
+    CU_TRY(h, cudaMemcpyAsync(h->an_ranks, ranks.data(), sizeof(long long) * ranks.size(), cudaMemcpyHostToDevice, stream));
+    radix_select_kernel<<<dim3(nframes, 3), 1024, 0, stream>>>(h->an_mag, h->an_rad, h->an_long, (int)npx, h->an_ranks, h->an_keys);
+    CU_TRY(h, cudaGetLastError());
+    std::vector<unsigned long long> keys((size_t)nframes * 12);
+    CU_TRY(h, cudaMemcpyAsync(keys.data(), h->an_keys, sizeof(unsigned long long) * keys.size(), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(h, cudaStreamSynchronize(stream));
+
+    const double nan = std::nan("");
+    for (int f = 0; f < nframes; ++f) {
+        const unsigned long long* k = keys.data() + (size_t)f * 12;
+        const long long nm = (long long)st[f].cnt[0], nr = (long long)st[f].cnt[2], nl = (long long)st[f].cnt[3];
+        if (out->counts) for (int q = 0; q < 4; ++q) out->counts[(size_t)f * 4 + q] = (int64_t)st[f].cnt[q];
+        if (out->mag_hi) out->mag_hi[f] = nm > 0 ? pct_f32(host_key_f32(k[0]), host_key_f32(k[1]), (int)nm, perc_hi) : (float)nan;
+        if (out->rad_lo) out->rad_lo[f] = nr > 0 ? pct_f64(host_key_f64(k[4]), host_key_f64(k[5]), nr, perc_lo) : nan;
+        if (out->rad_hi) out->rad_hi[f] = nr > 0 ? pct_f64(host_key_f64(k[6]), host_key_f64(k[7]), nr, perc_hi) : nan;
+        if (out->long_lo) out->long_lo[f] = nl > 0 ? pct_f64(host_key_f64(k[8]), host_key_f64(k[9]), nl, perc_lo) : nan;
+        if (out->long_hi) out->long_hi[f] = nl > 0 ? pct_f64(host_key_f64(k[10]), host_key_f64(k[11]), nl, perc_hi) : nan;
+        if (out->ang_mode) {
+            // scipy.stats.mode of np.round(ang, 2) over the non-zero entries: smallest value among ties
+            const unsigned* hst = ah.data() + (size_t)f * kAngBins;
+            unsigned best = 0; int bk = -1;
+            for (int b = 1; b < kAngBins; ++b) if (hst[b] > best) { best = hst[b]; bk = b; }
+            out->ang_mode[f] = bk < 0 ? (float)nan : (float)bk / 100.0f;
+        }
+    }
+    return TEEFLOW_OK;
+}
+
+// np.histogram of the non-zero entries of one analysed quantity (0 mag, 1 ang: float32 edges; 2 rad, 3 long:
+// float64 edges) with caller-provided numpy edges (np.linspace(first, last, nbins + 1)); freq_host[nframes][nbins]
+int teeflow_analysis_histogram(teeflow_handle h, int quantity, const void* edges_host, int nbins, int64_t* freq_host,
+                               void* stream_v) {
+    if (!h || !edges_host || !freq_host || quantity < 0 || quantity > 3 || nbins < 1 || nbins > 8192)
+        return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    if (h->an_frames < 1) return fail(h, TEEFLOW_ERR_STATE, "teeflow_analyze_clip has not been called");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int nframes = h->an_frames;
+    const size_t npx = (size_t)h->an_H * h->an_W;
+    const bool f64 = quantity >= 2;
+    const size_t esz = f64 ? 8 : 4;
+    if (!h->an_edges) CU_TRY(h, cudaMalloc(&h->an_edges, 8 * 8193));
+    if ((size_t)nframes * nbins > h->an_freq_cap) { CU_TRY(h, regrow(h->an_freq, (size_t)nframes * nbins)); h->an_freq_cap = (size_t)nframes * nbins; }
+    CU_TRY(h, cudaMemcpyAsync(h->an_edges, edges_host, esz * (nbins + 1), cudaMemcpyHostToDevice, stream));
+    CU_TRY(h, cudaMemsetAsync(h->an_freq, 0, sizeof(unsigned long long) * nframes * nbins, stream));
+    const int chunks = std::max(1, std::min((int)((npx + 256 * 8 - 1) / (256 * 8)), 64));
+    const dim3 grid(chunks, nframes);
+    const size_t smem = sizeof(unsigned) * nbins;
+    if (!f64) {
+        const float* e = (const float*)edges_host;
+        np_histogram_kernel<float><<<grid, 256, smem, stream>>>(quantity == 0 ? h->an_mag : h->an_ang, (int)npx,
+                                                                (const float*)h->an_edges, nbins, e[0], e[nbins], h->an_freq);
+    } else {
+        const double* e = (const double*)edges_host;
+        np_histogram_kernel<double><<<grid, 256, smem, stream>>>(quantity == 2 ? h->an_rad : h->an_long, (int)npx,
+                                                                 (const double*)h->an_edges, nbins, e[0], e[nbins], h->an_freq);
+    }
+    CU_TRY(h, cudaGetLastError());
+    static_assert(sizeof(unsigned long long) == sizeof(int64_t), "freq layout");
+    CU_TRY(h, cudaMemcpyAsync(freq_host, h->an_freq, sizeof(int64_t) * nframes * nbins, cudaMemcpyDeviceToHost, stream));
+    CU_TRY(h, cudaStreamSynchronize(stream));
     return TEEFLOW_OK;
 }
 

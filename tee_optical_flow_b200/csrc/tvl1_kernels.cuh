@@ -110,7 +110,7 @@ __device__ inline void advance_slot(const EngineParams& P, Slot& s, double err_s
         if (todo == NEXT_WARP) {
             s.warp++;
             if (s.warp < P.warps) { s.phase = PH_WARP; return; }
-            if (s.level == 0) { s.phase = PH_FINAL; return; }
+            if (s.level == 0) { s.phase = P.wase_w ? PH_WASE : PH_FINAL; return; }
             s.level--; s.phase = PH_LEVEL_INIT; return;
         }
     }
@@ -118,13 +118,13 @@ __device__ inline void advance_slot(const EngineParams& P, Slot& s, double err_s
 
 __device__ inline void start_pair(const EngineParams& P, Slot& s, int pair) {
     s.pair = pair; s.phase = PH_LEVEL_INIT; s.level = P.L - 1; s.warp = 0; s.n_outer = 0; s.n_inner = 0;
-    s.ucur = 0; s.pcur = 0; s.error = FLT_MAX;
+    s.ucur = 0; s.pcur = 0; s.error = FLT_MAX; s.bg = 0.f;
     for (int l = 0; l < kMaxLevels; ++l) { s.cnt[l][0] = 0; s.cnt[l][1] = 0; s.cnt[l][2] = 0; }
 }
 
 __device__ __forceinline__ int items_of(const EngineParams& P, int phase, int pair, int level) {
     if (phase == PH_IDLE || pair < 0) return 0;
-    if (phase == PH_FINAL) return P.lv[0].pw_items;
+    if (phase == PH_FINAL || phase == PH_WASE) return P.lv[0].pw_items;
     return phase == PH_INNER ? P.lv[level].in_items : P.lv[level].pw_items;
 }
 
@@ -385,8 +385,36 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return (uint32_t)lo | ((uint32_t)hi << 16);
 }
 
-// PH_FINAL: merge(u1,u2) * conversion_factor -> (H,W,2) f32 and/or f16 (calculate_optical_flow.py:600,403)
-__device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pair, int slot, int strip, int lane) {
+// PH_WASE: background = mean(masked_flow[masked_flow != 0]) with masked_flow = flow * bkgd[all N frames]
+// (calculate_optical_flow.py:649-652) == sum(w f [f != 0]) / sum(w [f != 0]) with w = sum_n bkgd[n]  (float64 sums)
+__device__ __forceinline__ void op_wase(const EngineParams& P, int ucur, int slot, int strip, int lane, double& sum,
+                                        double& cnt) {
+    const LevelGeom& g = P.lv[0];
+    const float2* U = P.U[ucur] + (size_t)slot * P.slot_px;
+    const float2* Wt = reinterpret_cast<const float2*>(P.wase_w);
+    const int x = (strip % g.pw_sx) * 32 + lane;
+    const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
+    sum = 0.0; cnt = 0.0;
+    if (x < g.W) {
+        for (int y = y0; y < y1; ++y) {
+            const unsigned q = (unsigned)(y * g.W + x);
+            const float2 u = U[q];
+            const float2 w = __ldg(Wt + q);
+            if (u.x != 0.f) { sum += (double)w.x * (double)u.x; cnt += (double)w.x; }
+            if (u.y != 0.f) { sum += (double)w.y * (double)u.y; cnt += (double)w.y; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_down_sync(0xffffffffu, sum, o);
+        cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+}
+
+// PH_FINAL: (merge(u1,u2) - background) * conversion_factor -> (H,W,2) f32 and/or f16
+// (calculate_optical_flow.py:659, 600, 403)
+__device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pair, float bg, int slot, int strip,
+                                         int lane) {
     const LevelGeom& g = P.lv[0];
     const size_t base = (size_t)slot * P.slot_px;
     const float2* U = P.U[ucur] + base;
@@ -398,8 +426,8 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
     for (int y = y0; y < y1; ++y) {
         const unsigned q = (unsigned)(y * g.W + x);
         float2 u = U[q];
-        u.x = u.x * P.out_scale;
-        u.y = u.y * P.out_scale;
+        u.x = (u.x - bg) * P.out_scale;
+        u.y = (u.y - bg) * P.out_scale;
         if (P.flow_f32) {
             P.flow_f32[(size_t)o0 * npx + q] = u;
             if (o1 >= 0) P.flow_f32[(size_t)o1 * npx + q] = u;
@@ -448,19 +476,24 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
         const int pair = sp->pair, phase = sp->phase, level = sp->level, ucur = sp->ucur, pcur = sp->pcur;
         const int n_items = s_prefix[slot + 1] - s_prefix[slot];
 
-        double err = 0.0;
+        double err = 0.0, aux = 0.0;
         switch (phase) {
             case PH_LEVEL_INIT: op_level_init(P, level, ucur, slot, strip, lane); break;
             case PH_WARP: op_warp(P, level, ucur, pair, slot, strip, lane, s_cubic); break;
             case PH_MEDIAN: op_median(P, level, ucur, slot, strip, lane); break;
             case PH_INNER: err = op_inner(P, level, ucur, pcur, slot, strip, lane); break;
-            case PH_FINAL: op_final(P, ucur, pair, slot, strip, lane); break;
+            case PH_WASE: op_wase(P, ucur, slot, strip, lane, err, aux); break;
+            case PH_FINAL: op_final(P, ucur, pair, sp->bg, slot, strip, lane); break;
             default: break;
         }
         __syncwarp();
         int last = 0;
         if (lane == 0) {
             if (phase == PH_INNER) P.partial[(size_t)slot * P.max_tiles + strip] = err;
+            if (phase == PH_WASE) {
+                P.partial[(size_t)slot * P.max_tiles + 2 * strip] = err;
+                P.partial[(size_t)slot * P.max_tiles + 2 * strip + 1] = aux;
+            }
             __threadfence();
             const unsigned ticket = atomicAdd(P.arrive + slot, 1u);
             last = (ticket == (unsigned)n_items - 1u);
@@ -469,16 +502,28 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
         if (last) {
             // last strip of this slot for this step: reduce the partials in strip order and advance the slot
             __threadfence();
-            double e = 0.0;
+            double e = 0.0, e2 = 0.0;
             if (phase == PH_INNER) {
                 const double* part = P.partial + (size_t)slot * P.max_tiles;
                 for (int t = lane; t < n_items; t += 32) e += __ldcg(part + t);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+            } else if (phase == PH_WASE) {
+                const double* part = P.partial + (size_t)slot * P.max_tiles;
+                for (int t = lane; t < n_items; t += 32) { e += __ldcg(part + 2 * t); e2 += __ldcg(part + 2 * t + 1); }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    e += __shfl_down_sync(0xffffffffu, e, o);
+                    e2 += __shfl_down_sync(0xffffffffu, e2, o);
+                }
             }
             if (lane == 0) {
                 Slot n = *sp;
-                if (n.phase == PH_FINAL) {
+                if (n.phase == PH_WASE) {
+                    n.bg = (float)(e / e2);          // 0/0 -> NaN, like np.mean of an empty selection
+                    P.bg_out[n.pair] = n.bg;
+                    n.phase = PH_FINAL;
+                } else if (n.phase == PH_FINAL) {
                     int* co = P.counters_out + (size_t)n.pair * kMaxLevels * 3;
                     for (int l = 0; l < kMaxLevels; ++l) { co[l * 3] = n.cnt[l][0]; co[l * 3 + 1] = n.cnt[l][1]; co[l * 3 + 2] = n.cnt[l][2]; }
                     const int next = atomicAdd(P.next_pair, 1);

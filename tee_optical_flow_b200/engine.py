@@ -229,6 +229,88 @@ class TVL1Engine:
             float(np.float32(out_scale)), C.c_void_p(stream)))
         return f32, f16
 
+    # ------------------------------------------------------------------ WASE background compensation
+    def set_wase_masks(self, bkgd_mask) -> None:
+        """bkgd_comp='WASE' (calculate_optical_flow.py:649-652): `bkgd_mask` is mask_dict['bkgd'], (N, H, W, 2) bool
+        for ALL frames (numpy or CUDA torch tensor).  Builds the weight map w = sum_n bkgd[n] on the GPU and makes
+        every following calc subtract the per-pair scalar mean(flow*bkgd != 0).  None switches it off."""
+        import torch
+        if bkgd_mask is None:
+            self._wase_w = None
+            self._check(self._lib.teeflow_set_wase(self._h, None, 0, 0))
+            return
+        m = bkgd_mask if isinstance(bkgd_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bkgd_mask))
+        if m.dim() != 4 or m.shape[-1] != 2:
+            raise OpticalFlowCalculationError("bkgd mask must be (N, H, W, 2)")
+        m = m.to(device=f"cuda:{self.device}").contiguous().view(torch.uint8) if m.dtype == torch.bool else \
+            m.to(device=f"cuda:{self.device}", dtype=torch.uint8).contiguous()
+        N, H, W, _ = m.shape
+        w = torch.empty((H, W, 2), dtype=torch.float32, device=m.device)
+        stream = torch.cuda.current_stream(m.device).cuda_stream
+        self._check(self._lib.teeflow_wase_weights(self._h, m.data_ptr(), N, H, W, w.data_ptr(), C.c_void_p(stream)))
+        torch.cuda.current_stream(m.device).synchronize()
+        self._wase_w = w                      # keep the caller-owned buffer alive
+        self._check(self._lib.teeflow_set_wase(self._h, w.data_ptr(), H, W))
+
+    def last_backgrounds(self) -> np.ndarray:
+        st = _lib.TeeflowStats()
+        self._check(self._lib.teeflow_get_stats(self._h, C.byref(st)))
+        out = np.zeros(max(st.n_pairs, 1), np.float32)
+        self._check(self._lib.teeflow_get_backgrounds(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), len(out)))
+        return out[:st.n_pairs]
+
+    # ------------------------------------------------------------------ decomposition + per-frame reductions
+    def analyze_clip(self, flow_f16, mask, centroids, nframes: int, perc_lo: float = 1, perc_hi: float = 99) -> dict:
+        """Per-frame waveforms of one label (analysis.py:215-327, cardiac_cycle_detection.py:100-116) on the GPU.
+        flow_f16: (N,H,W,2) float16 stored flow; mask: (N,H,W,2) bool; centroids: (nframes,2) float64 (row, col)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        f = flow_f16 if isinstance(flow_f16, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(flow_f16))
+        m = mask if isinstance(mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(mask))
+        if f.dtype != torch.float16 or f.dim() != 4 or f.shape[-1] != 2 or tuple(m.shape) != tuple(f.shape):
+            raise OpticalFlowCalculationError("flow must be (N,H,W,2) float16 and mask (N,H,W,2) bool")
+        f = f.to(dev).contiguous()
+        m = (m.to(dev).contiguous().view(torch.uint8) if m.dtype == torch.bool else m.to(dev, torch.uint8).contiguous())
+        N, H, W, _ = f.shape
+        if not (1 <= nframes <= N):
+            raise OpticalFlowCalculationError("nframes out of range")
+        cent = np.ascontiguousarray(centroids, np.float64)
+        if cent.shape != (nframes, 2):
+            raise OpticalFlowCalculationError("centroids must be (nframes, 2) float64 (row, col)")
+        res = dict(mag_hi=np.empty(nframes, np.float32), ang_mode=np.empty(nframes, np.float32),
+                   rad_hi=np.empty(nframes), rad_lo=np.empty(nframes), long_hi=np.empty(nframes),
+                   long_lo=np.empty(nframes), counts=np.empty((nframes, 4), np.int64))
+        out = _lib.TeeflowAnalysis()
+        for k, a in res.items():
+            ct = {np.dtype(np.float32): C.c_float, np.dtype(np.float64): C.c_double, np.dtype(np.int64): C.c_int64}[a.dtype]
+            setattr(out, k, a.ctypes.data_as(C.POINTER(ct)))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        self._check(self._lib.teeflow_analyze_clip(self._h, f.data_ptr(), m.data_ptr(),
+                                                   cent.ctypes.data_as(C.POINTER(C.c_double)), nframes, H, W,
+                                                   float(perc_lo), float(perc_hi), C.byref(out), C.c_void_p(stream)))
+        for k in ("mag_min", "mag_max", "ang_min", "ang_max"):
+            res[k] = np.float32(getattr(out, k))
+        for k in ("rad_min", "rad_max", "long_min", "long_max"):
+            res[k] = np.float64(getattr(out, k))
+        res["nframes"] = nframes
+        return res
+
+    def analysis_histogram(self, quantity: str, nframes: int, first, last, nbins: int = 1000):
+        """np.histogram(non-zero, bins=nbins, range=(first, last)) per frame for 'mag' | 'ang' | 'rad' | 'long' of the
+        last analyze_clip.  Returns (freq[nframes, nbins] int64 WITHOUT the reference's +1, edges)."""
+        import torch
+        qi = {"mag": 0, "ang": 1, "rad": 2, "long": 3}[quantity]
+        dt = np.float32 if qi < 2 else np.float64
+        first, last = dt(first), dt(last)
+        if first == last:                       # numpy: first_edge -= 0.5; last_edge += 0.5
+            first, last = dt(first - dt(0.5)), dt(last + dt(0.5))
+        edges = np.linspace(first, last, nbins + 1, endpoint=True, dtype=dt)
+        freq = np.empty((nframes, nbins), np.int64)
+        stream = torch.cuda.current_stream(torch.device("cuda", self.device)).cuda_stream
+        self._check(self._lib.teeflow_analysis_histogram(self._h, qi, edges.ctypes.data, nbins,
+                                                         freq.ctypes.data_as(C.POINTER(C.c_int64)), C.c_void_p(stream)))
+        return freq, edges
+
     # ------------------------------------------------------------------ accounting
     def last_counters(self) -> Tuple[np.ndarray, dict]:
         """(counters[n_pairs, n_levels, 3] = inner iterations / median passes / warps executed per level,

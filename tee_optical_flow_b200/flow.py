@@ -1,0 +1,252 @@
+"""The reference's producer API for the TV-L1 path, same names / arguments / error behaviour
+(optical_flow/calculate_optical_flow.py), with the per-pair OpenCV call replaced by the batched B200 engine.
+
+    calculate_optical_flow(saliency_1, saliency_2, mask_dict, OF_model, bkgd_comp, OF_algo)   :627-660
+    process_frames(frames, ...)      array-level form of process_video (no DICOM / HDF5 libraries needed)
+    process_video(dcm_path, save_path, segmentor_model, ...)                                  :478-625
+    process_folder(dcm_folder, save_folder, segmentor_model, nchunks, chunk_index, ...)       :243-290
+
+Out of scope here: SAM mask prediction, DICOM parsing and waveform loading are inputs to this
+path; process_video imports pydicom / h5py lazily and raises a clear error when they are missing.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import traceback
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+from .config import OpticalFlowCalculationConfig, default_optical_flow_config
+from .engine import TVL1Engine
+from .exceptions import ConfigurationError, DICOMReadError, OpticalFlowCalculationError
+
+logger = logging.getLogger(__name__)
+
+
+# ------------------------------------------------------------------------------------------------ frame prep
+def rgb2gray(rgb: np.ndarray) -> np.ndarray:
+    """skimage.color.rgb2gray: float image in [0,1], luminance 0.2125 R + 0.7154 G + 0.0721 B."""
+    a = np.asarray(rgb)
+    if a.dtype == np.uint8:
+        a = a.astype(np.float64) / 255.0          # skimage img_as_float
+    else:
+        a = a.astype(np.float64)
+    coeffs = np.array([0.2125, 0.7154, 0.0721], dtype=np.float64)
+    return a @ coeffs
+
+
+def img2uint8(img: np.ndarray) -> np.ndarray:
+    """optical_flow_utils.py:30-31: img_as_ubyte((img - min) / max)  (sic: divides by max, not by the range)."""
+    x = (img - np.min(img)) / np.max(img)
+    return np.clip(np.rint(x * 255.0), 0, 255).astype(np.uint8)   # skimage img_as_ubyte of a float image in [0,1]
+
+
+def prepare_frames(nparr: np.ndarray) -> np.ndarray:
+    """the `no_saliency=True` input stage of the pair loop (:588): img2uint8(rgb2gray(frame)) per frame."""
+    if nparr.ndim == 3:
+        nparr = np.stack([nparr] * 3, axis=-1)    # gray2rgb (:536)
+    return np.stack([img2uint8(rgb2gray(nparr[i])) for i in range(nparr.shape[0])])
+
+
+# ------------------------------------------------------------------------------------------------ per pair
+def calculate_optical_flow(saliency_1: np.ndarray, saliency_2: np.ndarray, mask_dict: Dict[str, np.ndarray],
+                           OF_model: Any, bkgd_comp: str = 'none', OF_algo: str = 'TVL1') -> Optional[np.ndarray]:
+    """Same contract as the reference (:627-660).  `OF_model` is a TVL1Engine (or anything with .calc)."""
+    if OF_algo == 'TVL1':
+        if bkgd_comp not in ('WASE', 'none'):
+            error_msg = f'bkgd_comp value must be [WASE, none], got {bkgd_comp}!'
+            logger.error(error_msg)
+            raise OpticalFlowCalculationError(error_msg)
+        if isinstance(OF_model, TVL1Engine):
+            OF_model.set_wase_masks(mask_dict['bkgd'] if bkgd_comp == 'WASE' else None)
+            try:
+                return OF_model.calc(saliency_1, saliency_2, None)      # background already subtracted on the GPU
+            finally:
+                OF_model.set_wase_masks(None)
+        flow = OF_model.calc(saliency_1, saliency_2, None)
+    elif OF_algo == 'deepflow':
+        raise OpticalFlowCalculationError("OF_algo='deepflow' is outside this engine (TV-L1 path only)")
+    else:
+        error_msg = 'OF_algo only supports deepflow or TVL1'
+        logger.error(error_msg)
+        raise OpticalFlowCalculationError(error_msg)
+    background = 0
+    if bkgd_comp == 'WASE':
+        masked_flow = flow * mask_dict['bkgd']
+        background = np.mean(masked_flow[masked_flow != 0])
+    return flow - background
+
+
+# ------------------------------------------------------------------------------------------------ per clip
+def process_frames(frames: np.ndarray, mask_dict: Optional[Dict[str, np.ndarray]] = None,
+                   pixel_spacing: Optional[float] = None, frame_rate: Optional[float] = None,
+                   mode: str = 'RVIO_2class', bkgd_comp: str = 'none', no_saliency: bool = True,
+                   OF_algo: str = 'TVL1', save_mask_subset: Optional[List[str]] = None,
+                   config: Optional[OpticalFlowCalculationConfig] = None, engine: Optional[TVL1Engine] = None,
+                   frames_are_prepared: bool = False, patient_id: str = '', heart_rate: float = 0) -> Dict[str, Any]:
+    """Array-level process_video: frames (N,H,W[,3]) -> the HDF5 layout of _save_optical_flow_to_hdf5 (:370-475)
+    as an in-memory dict: datasets 'echo' (N,H,W) f16, 'flow' (N,H,W,2) f16, one bool dataset per mask label, and
+    'attrs' (the attributes of the 'flow' dataset that OpticalFlowDataset reads, optical_flow_dataset.py:45-111).
+    """
+    if config is None:
+        config = default_optical_flow_config()
+    if mode == 'otsu':
+        if bkgd_comp != 'none':
+            raise ConfigurationError(f'bkgd_comp {bkgd_comp} is not supported in mode=otsu, can only support bkgd_comp=none')
+        if save_mask_subset is not None:
+            raise ConfigurationError('In mode=otsu, save_mask_subset must be None')
+    elif mode not in ('A4C', 'RVIO_2class'):
+        raise ConfigurationError(f'Input for mode must be [A4C, otsu, RVIO_2class], not {mode}.')
+    if OF_algo != 'TVL1':
+        raise OpticalFlowCalculationError('OF_algo only supports deepflow or TVL1' if OF_algo != 'deepflow'
+                                          else "OF_algo='deepflow' is outside this engine (TV-L1 path only)")
+    if bkgd_comp not in ('WASE', 'none'):
+        raise OpticalFlowCalculationError(f'bkgd_comp value must be [WASE, none], got {bkgd_comp}!')
+    if not no_saliency:
+        raise OpticalFlowCalculationError("saliency input (cv2.saliency) is a 'next' row (SURVEY.md §8f); "
+                                          "pass no_saliency=True")
+    frames = np.asarray(frames)
+    if frames.shape[0] < 2:
+        raise OpticalFlowCalculationError('need at least two frames')
+    mask_dict = mask_dict or {}
+    if bkgd_comp == 'WASE' and 'bkgd' not in mask_dict:
+        raise ConfigurationError("bkgd_comp='WASE' needs mask_dict['bkgd']")
+
+    gray_u8 = frames if frames_are_prepared else prepare_frames(frames)
+    if gray_u8.dtype != np.uint8 or gray_u8.ndim != 3:
+        raise OpticalFlowCalculationError('prepared frames must be (N,H,W) uint8')
+    conversion_factor = 1.0 if (pixel_spacing is None or frame_rate is None) else pixel_spacing * frame_rate   # :538-541
+
+    own = engine is None
+    if own:
+        engine = TVL1Engine(**config.tvl1_params())
+    try:
+        engine.set_wase_masks(mask_dict['bkgd'] if bkgd_comp == 'WASE' else None)
+        # pair loop (:584-597) + copy of the last flow (:599) + * conversion_factor (:600) + astype(float16) (:403)
+        _, flow16 = engine.calc_clip(gray_u8, out_scale=conversion_factor, duplicate_last=True, want_f32=False,
+                                     want_f16=True)
+        counters, info = engine.last_counters()
+    finally:
+        engine.set_wase_masks(None)
+        if own:
+            engine.close()
+
+    echo = (rgb2gray(frames) if frames.ndim == 4 else frames.astype(np.float64) / (255.0 if frames.dtype == np.uint8 else 1.0))
+    saved = [k for k in mask_dict if save_mask_subset is None or k in save_mask_subset]
+    out: Dict[str, Any] = {'echo': echo.astype(np.float16), 'flow': flow16}
+    for k in saved:
+        out[k] = np.asarray(mask_dict[k])
+    out['attrs'] = {
+        'frame_rate': frame_rate, 'nframes': int(frames.shape[0]), 'pixel_spacing': pixel_spacing, 'ID': patient_id,
+        'HR': heart_rate, 'no_saliency': no_saliency, 'mode': mode,
+        'units_converted': (pixel_spacing is not None and frame_rate is not None), 'waveforms_present': False,
+        'labels': saved,
+    }
+    out['_engine_info'] = info
+    out['_counters'] = counters
+    return out
+
+
+def save_hdf5(save_path: str, result: Dict[str, Any]) -> None:
+    """Writes process_frames' dict with the reference's dataset names, dtypes and gzip-9 (:399-472)."""
+    try:
+        import h5py
+    except ImportError as e:  # pragma: no cover
+        raise OpticalFlowCalculationError("h5py is not installed: the HDF5 container cannot be written here; "
+                                          "use the dict returned by process_frames") from e
+    if os.path.exists(save_path):
+        os.remove(save_path)
+    with h5py.File(save_path, 'w') as f:
+        f.create_dataset('echo', data=result['echo'], compression='gzip', compression_opts=9)
+        d = f.create_dataset('flow', data=result['flow'], compression='gzip', compression_opts=9)
+        for k in result['attrs']['labels']:
+            f.create_dataset(k, data=result[k], compression='gzip', compression_opts=9)
+        for k, v in result['attrs'].items():
+            d.attrs[k] = v if v is not None else np.nan
+
+
+def process_video(dcm_path: str, save_path: str, segmentor_model: Any, verbose: bool = True, mode: str = 'A4C',
+                  bkgd_comp: str = 'none', flipLR: bool = False, no_saliency: bool = False, OF_algo: str = 'TVL1',
+                  save_mask_subset: Optional[List[str]] = None, include_waveforms: bool = False,
+                  waveform_folder: Optional[str] = None,
+                  config: Optional[OpticalFlowCalculationConfig] = None, mask_fn=None) -> None:
+    """Signature of the reference (:478-483).  DICOM reading and HDF5 writing need pydicom / h5py; the masks come
+    from `mask_fn(nparr, segmentor_model, mode, config)` (the reference's predict_movie, SAM -- out of scope)."""
+    if config is None:
+        config = default_optical_flow_config()
+    if mode == 'otsu':
+        if bkgd_comp != 'none':
+            raise ConfigurationError(f'bkgd_comp {bkgd_comp} is not supported in mode=otsu, can only support bkgd_comp=none')
+        if save_mask_subset is not None:
+            raise ConfigurationError('In mode=otsu, save_mask_subset must be None')
+    try:
+        import pydicom as dcm
+    except ImportError as e:
+        raise DICOMReadError(f'Failed to read DICOM file: {dcm_path} (pydicom is not installed)') from e
+    try:
+        ds = dcm.dcmread(dcm_path)
+        nparr = ds.pixel_array
+    except Exception as e:
+        raise DICOMReadError(f'Failed to read DICOM file: {dcm_path}') from e
+    if flipLR:
+        nparr = np.flip(nparr, axis=2)
+    if mask_fn is None:
+        raise ConfigurationError('mask_fn is required: mask prediction (SAM / Otsu) is an input of this path')
+    mask_dict = mask_fn(nparr, segmentor_model, mode, config)
+    try:
+        frame_rate = float(ds.CineRate)
+        pixel_spacing = float(ds.SequenceOfUltrasoundRegions[0].PhysicalDeltaX)
+    except Exception:
+        frame_rate = pixel_spacing = None
+    result = process_frames(nparr, mask_dict, pixel_spacing, frame_rate, mode, bkgd_comp, no_saliency, OF_algo,
+                            save_mask_subset, config, patient_id=str(getattr(ds, 'PatientID', '')),
+                            heart_rate=getattr(ds, 'HeartRate', 0))
+    save_hdf5(save_path, result)
+
+
+def chunk_bounds(total: int, nchunks: int, chunk_index: int):
+    """The reference's chunking (:266-269): split = total // nchunks; chunk c owns [c*split, (c+1)*split); the
+    remainder is dropped.  `--nchunks` maps onto GPU ranks: rank r == chunk r."""
+    split = total // nchunks
+    return chunk_index * split, (chunk_index + 1) * split
+
+
+def process_folder(dcm_folder: str, save_folder: str, segmentor_model: Any, nchunks: int = 10, chunk_index: int = 0,
+                   mode: str = 'RVIO_2class', bkgd_comp: str = 'none', flipLR: bool = False, verbose: bool = True,
+                   recalculate: bool = False, no_saliency: bool = True, OF_algo: str = 'TVL1',
+                   save_mask_subset: Optional[List[str]] = None, include_waveforms: bool = False,
+                   waveform_folder: Optional[str] = None, pixel_spacing: Optional[float] = None,
+                   frame_rate: Optional[float] = None, process_subset: bool = False,
+                   file_subset_list: List[str] = [], mask_fn=None) -> None:
+    """Signature and semantics of the reference (:243-290): chunked, skip-if-exists, per-file errors are logged
+    and swallowed so that one bad clip does not kill the batch."""
+    os.makedirs(save_folder, exist_ok=True)
+    file_list = os.listdir(dcm_folder)
+    if process_subset:
+        if len(file_subset_list) == 0:
+            print('ERROR! File subset list is empty!')
+            return
+        file_list = [f for f in file_list if f in file_subset_list]
+    if include_waveforms and waveform_folder is None:
+        print('ERROR if include_waveform is selected, must define waveform_folder!')
+        return
+    lo, hi = chunk_bounds(len(file_list), nchunks, chunk_index)
+    for i in range(lo, hi):
+        filename = file_list[i]
+        save_path = os.path.join(save_folder, filename[:-3] + 'hdf5')
+        if os.path.exists(save_path) and not recalculate:
+            continue
+        if filename[-3:] != 'dcm':
+            logger.warning(f'File extension must be dcm, found {filename[-3:]}, skipping')
+            continue
+        try:
+            process_video(os.path.join(dcm_folder, filename), save_path, segmentor_model, verbose=verbose, mode=mode,
+                          bkgd_comp=bkgd_comp, flipLR=flipLR, no_saliency=no_saliency, OF_algo=OF_algo,
+                          save_mask_subset=save_mask_subset, include_waveforms=include_waveforms,
+                          waveform_folder=waveform_folder, mask_fn=mask_fn)
+        except Exception as e:
+            logger.error(f'Error processing {filename}: {e}')
+            if verbose:
+                traceback.print_exc()
