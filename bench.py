@@ -106,7 +106,7 @@ def cpu_reference_rate(frames: np.ndarray, n_pairs: int, repeats: int = 1):
     from oracle import tvl1_oracle as O
     O.build()
     model, kind_name = O.create_reference_model()
-    cores = os.cpu_count() or 1
+    cores = O.set_threads(0)          # all host cores (torchrun exports OMP_NUM_THREADS=1)
     best = None
     for _ in range(repeats):
         t = time.perf_counter()

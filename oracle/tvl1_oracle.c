@@ -43,6 +43,21 @@
 
 #define TF_EXPORT __attribute__((visibility("default")))
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* number of OpenMP threads the oracle uses (launchers such as torchrun export OMP_NUM_THREADS=1); returns the
+ * value in effect */
+TF_EXPORT int oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 typedef struct {
     double tau;            /* 0.25 */
     double lambda;         /* 0.15 */

@@ -67,8 +67,15 @@ def lib() -> C.CDLL:
         L.oracle_cubic_table.argtypes = [fp]
         L.oracle_scaled_size.restype = None
         L.oracle_scaled_size.argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.oracle_set_threads.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
+
+
+def set_threads(n: int = 0) -> int:
+    """OpenMP threads used by the oracle (0 = all host cores); returns the value in effect."""
+    return lib().oracle_set_threads(int(n) if n > 0 else (os.cpu_count() or 1))
 
 
 def _fp(a: np.ndarray):
