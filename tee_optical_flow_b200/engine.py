@@ -229,6 +229,28 @@ class TVL1Engine:
             float(np.float32(out_scale)), C.c_void_p(stream)))
         return f32, f16
 
+    def calc_batch(self, clips, out_scale: float = 1.0, duplicate_last: bool = True, want_f32: bool = False,
+                   want_f16: bool = True):
+        """A batch of equally shaped clips (B, N, H, W) on one GPU (BASELINE config 4, one rank's share): all
+        B*(N-1) pairs go through ONE scheduler run, so slots freed by one clip are refilled with pairs of the next
+        (no drain between clips).  Returns (f32, f16) shaped (B, N_out, H, W, 2)."""
+        import torch
+        if not (isinstance(clips, torch.Tensor) and clips.is_cuda and clips.dim() == 4):
+            raise OpticalFlowCalculationError("clips must be a CUDA tensor (B, N, H, W)")
+        B, N, H, W = clips.shape
+        if N < 2:
+            raise OpticalFlowCalculationError("a clip needs at least 2 frames")
+        n_out = N if duplicate_last else N - 1
+        a = (np.arange(B)[:, None] * N + np.arange(N - 1)[None, :]).ravel().astype(np.int32)
+        o = (np.arange(B)[:, None] * n_out + np.arange(N - 1)[None, :]).ravel().astype(np.int32)
+        d = np.full(B * (N - 1), -1, np.int32)
+        if duplicate_last:
+            d[N - 2::N - 1] = o[N - 2::N - 1] + 1
+        f32, f16 = self.calc_pairs_device(clips.reshape(B * N, H, W), a, a + 1, o, d, n_out=B * n_out,
+                                          out_scale=out_scale, want_f32=want_f32, want_f16=want_f16)
+        rs = lambda t: None if t is None else t.view(B, n_out, H, W, 2)
+        return rs(f32), rs(f16)
+
     # ------------------------------------------------------------------ WASE background compensation
     def set_wase_masks(self, bkgd_mask) -> None:
         """bkgd_comp='WASE' (calculate_optical_flow.py:649-652): `bkgd_mask` is mask_dict['bkgd'], (N, H, W, 2) bool

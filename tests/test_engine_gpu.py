@@ -228,3 +228,33 @@ def test_exact_division_matches_ieee(engine, mode):
     bad = C.c_int64(-1)
     rc = engine._lib.teeflow_selftest_division(engine._h, mode, 1 << 32, 1234 + mode, C.byref(bad))
     assert rc == 0 and bad.value == 0
+
+
+def test_batch_of_clips_equals_per_clip():
+    """BASELINE config 4 (one rank's share): several clips through one scheduler run, slots refilled across clips"""
+    import torch
+    from tee_optical_flow_b200.synth import make_clip
+    clips = np.stack([make_clip(seed=s, n_frames=6, H=64, W=96, peak_disp=4.0, period=6.0) for s in (20, 21, 22)])
+    with _fresh(max_slots=4) as eng:
+        _, b16 = eng.calc_batch(torch.from_numpy(clips).cuda(), out_scale=1.25)
+        b16 = b16.cpu().numpy()
+        assert b16.shape == (3, 6, 64, 96, 2)
+        for i in range(3):
+            _, c16 = eng.calc_clip(clips[i], out_scale=1.25, want_f32=False, want_f16=True)
+            assert np.array_equal(b16[i], c16)
+
+
+def test_long_clip_config_1024_7scales_10warps(oracle):
+    """BASELINE config 5 geometry: 1024x1024, nscales=7, warps=10 -- one pair against the oracle, bit for bit"""
+    from tee_optical_flow_b200.synth import make_clip
+    fr = make_clip(seed=30, n_frames=2, H=1024, W=1024, peak_disp=4.0, period=10.0)
+    with _fresh(nscales=7, warps=10) as eng:
+        assert eng.level_sizes(1024, 1024) == [(1024, 1024), (819, 819), (655, 655), (524, 524), (419, 419),
+                                               (335, 335), (268, 268)]
+        flow = eng.calc(fr[0], fr[1])
+        counters, _ = eng.last_counters()
+    om = oracle.OracleDualTVL1(nscales=7, warps=10, err_mode=1)
+    ref = om.calc(fr[0], fr[1])
+    assert np.all(flow == ref)
+    assert np.array_equal(counters[0], om.last_counters)
+    assert (counters[0, :, 2] == 10).all()

@@ -1,0 +1,74 @@
+"""CPU tests of the host-side API mirror (flow.py): frame prep arithmetic, chunking, error behaviour that does not
+need a GPU."""
+import numpy as np
+import pytest
+
+
+def test_img2uint8_follows_reference_formula():
+    """optical_flow_utils.py:30-31: img_as_ubyte((img - min) / max) -- divides by max, not by the range"""
+    from tee_optical_flow_b200.flow import img2uint8, rgb2gray
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 256, (12, 14, 3), dtype=np.uint8)
+    g = rgb2gray(rgb)
+    want_gray = (rgb.astype(np.float64) / 255.0) @ np.array([0.2125, 0.7154, 0.0721])
+    assert np.allclose(g, want_gray, rtol=0, atol=1e-15)
+    out = img2uint8(g)
+    want = np.clip(np.rint(((g - g.min()) / g.max()) * 255.0), 0, 255).astype(np.uint8)
+    assert out.dtype == np.uint8 and np.array_equal(out, want)
+    assert out.max() < 255 or g.min() == 0        # the (sic) formula never reaches 255 unless min == 0
+
+
+def test_prepare_frames_gray_and_rgb():
+    from tee_optical_flow_b200.flow import prepare_frames
+    rng = np.random.default_rng(1)
+    gray = rng.integers(0, 256, (3, 8, 9), dtype=np.uint8)
+    a = prepare_frames(gray)
+    b = prepare_frames(np.stack([gray] * 3, axis=-1))
+    assert a.shape == (3, 8, 9) and a.dtype == np.uint8 and np.array_equal(a, b)
+
+
+def test_chunk_bounds_reexported():
+    from tee_optical_flow_b200.flow import chunk_bounds
+    assert chunk_bounds(23, 4, 3) == (15, 20)
+
+
+def test_process_frames_validates_before_touching_the_gpu():
+    from tee_optical_flow_b200.exceptions import ConfigurationError, OpticalFlowCalculationError
+    from tee_optical_flow_b200.flow import process_frames
+    fr = np.zeros((3, 16, 16), np.uint8)
+    with pytest.raises(ConfigurationError):
+        process_frames(fr, mode='otsu', bkgd_comp='WASE', frames_are_prepared=True)
+    with pytest.raises(ConfigurationError):
+        process_frames(fr, mode='otsu', save_mask_subset=['rv'], frames_are_prepared=True)
+    with pytest.raises(ConfigurationError):
+        process_frames(fr, mode='nope', frames_are_prepared=True)
+    with pytest.raises(OpticalFlowCalculationError):
+        process_frames(fr, OF_algo='farneback', frames_are_prepared=True)
+    with pytest.raises(OpticalFlowCalculationError):
+        process_frames(fr, bkgd_comp='median', frames_are_prepared=True)
+    with pytest.raises(ConfigurationError):
+        process_frames(fr, bkgd_comp='WASE', frames_are_prepared=True)      # no 'bkgd' mask
+
+
+def test_process_folder_swallows_per_file_errors(tmp_path, caplog):
+    """a failed clip must not kill the batch (calculate_optical_flow.py:281-284)"""
+    from tee_optical_flow_b200.flow import process_folder
+    d = tmp_path / "dcm"; d.mkdir()
+    (d / "a.dcm").write_bytes(b"not a dicom")
+    (d / "b.txt").write_text("x")
+    process_folder(str(d), str(tmp_path / "out"), None, nchunks=1, chunk_index=0, verbose=False, mask_fn=lambda *a: {})
+    assert (tmp_path / "out").is_dir() and not list((tmp_path / "out").iterdir())
+
+
+def test_downstream_restatements_selfcheck():
+    """the restated third-party helpers of the parity harness behave like their originals on known cases"""
+    from oracle import downstream_ref as R
+    x = np.sin(np.linspace(0, 6 * np.pi, 60)) + 0.01 * np.cos(np.linspace(0, 90, 60))
+    pk = R.peak_indexes(x, thres=0.5, min_dist=5)
+    assert pk.tolist() == [5, 25, 44] or all(abs(a - b) <= 1 for a, b in zip(pk.tolist(), [5, 25, 44]))
+    assert R.peak_indexes(np.ones(10)).size == 0
+    assert R.find_start_stop(np.array([0, 1, 2, 5, 6, 9])) == [[0, 2], [5, 6], [9, 9]]
+    y = R.spectral_smooth(x, 0.3, 20)
+    assert y.shape == x.shape and np.abs(y - np.sin(np.linspace(0, 6 * np.pi, 60))).max() < 0.1
+    with pytest.raises(ValueError):
+        R.spectral_smooth(np.ones(10), 0.3, 20)
