@@ -35,8 +35,7 @@ struct teeflow_engine {
     size_t cap_slot_px = 0, cap_tiles = 0, cap_pairs = 0;
     float* pyrI = nullptr;
     float4* pyrG = nullptr;
-    float2 *U[2] = {nullptr, nullptr}, *PX[2] = {nullptr, nullptr}, *PY[2] = {nullptr, nullptr};
-    float4* COEF = nullptr;
+    float2* planes = nullptr;  // [S][kPlanes][slot_px]
     Slot* slots = nullptr;     // [2][S]
     unsigned* arrive = nullptr;
     double* partial = nullptr;
@@ -164,8 +163,7 @@ int teeflow_destroy(teeflow_handle h) {
     if (!h) return TEEFLOW_OK;
     cudaSetDevice(h->device);
     cudaFree(h->pyrI); cudaFree(h->pyrG);
-    for (int i = 0; i < 2; ++i) { cudaFree(h->U[i]); cudaFree(h->PX[i]); cudaFree(h->PY[i]); }
-    cudaFree(h->COEF); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
+    cudaFree(h->planes); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
     cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg);
     cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
     cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
@@ -295,12 +293,7 @@ static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_strid
         h->cap_frames = n_frames; h->cap_pyr_stride = pyr_stride;
     }
     if ((size_t)S * slot_px > (size_t)h->cap_slots * h->cap_slot_px) {
-        for (int i = 0; i < 2; ++i) {
-            CU_TRY(h, regrow(h->U[i], (size_t)S * slot_px));
-            CU_TRY(h, regrow(h->PX[i], (size_t)S * slot_px));
-            CU_TRY(h, regrow(h->PY[i], (size_t)S * slot_px));
-        }
-        CU_TRY(h, regrow(h->COEF, (size_t)S * slot_px));
+        CU_TRY(h, regrow(h->planes, (size_t)S * slot_px * kPlanes));
         h->cap_slots = S; h->cap_slot_px = slot_px;
     }
     if ((size_t)S * max_tiles > h->cap_tiles) {
@@ -377,8 +370,9 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     int rc = ensure_workspace(h, (size_t)n_frames, (size_t)off, S, (size_t)P.slot_px, (size_t)P.max_tiles, (size_t)n_pairs);
     if (rc) return rc;
     P.pyrI = h->pyrI; P.pyrG = h->pyrG;
-    for (int i = 0; i < 2; ++i) { P.U[i] = h->U[i]; P.PX[i] = h->PX[i]; P.PY[i] = h->PY[i]; P.slots[i] = h->slots + (size_t)i * kMaxSlots; }
-    P.COEF = h->COEF; P.arrive = h->arrive; P.partial = h->partial;
+    for (int i = 0; i < 2; ++i) P.slots[i] = h->slots + (size_t)i * kMaxSlots;
+    P.planes = h->planes; P.slot_stride = (long long)kPlanes * P.slot_px;
+    P.arrive = h->arrive; P.partial = h->partial;
     P.next_pair = h->ctl; P.pairs_done = h->ctl + 1;
     P.pair_a = h->pair_lists; P.pair_b = h->pair_lists + h->cap_pairs;
     P.out_index = h->pair_lists + 2 * h->cap_pairs; P.dup_index = h->pair_lists + 3 * h->cap_pairs;

@@ -129,15 +129,20 @@ __device__ __forceinline__ int items_of(const EngineParams& P, int phase, int pa
 }
 
 // ------------------------------------------------------------------------------------------------ strip ops
+// All slot planes are addressed as  slot base (one 64-bit pointer) + 32-bit float2 element index.
+__device__ __forceinline__ float2* slot_base(const EngineParams& P, int slot) {
+    return P.planes + (size_t)slot * (size_t)P.slot_stride;
+}
+__device__ __forceinline__ unsigned plane_at(const EngineParams& P, unsigned plane) { return plane * (unsigned)P.slot_px; }
+
 // PH_LEVEL_INIT: u = 0 (coarsest) or u = resize(u_coarse, INTER_LINEAR) * (1/scaleStep); p = 0
 __device__ __forceinline__ void op_level_init(const EngineParams& P, int level, int ucur, int slot, int strip, int lane) {
     const LevelGeom& g = P.lv[level];
-    const size_t base = (size_t)slot * P.slot_px;
+    float2* SB = slot_base(P, slot);
     const bool coarsest = (level == P.L - 1);
-    float2* Ud = P.U[coarsest ? 0 : (ucur ^ 1)] + base;
-    const float2* Us = P.U[ucur] + base;
-    float2* PXd = P.PX[0] + base;
-    float2* PYd = P.PY[0] + base;
+    const unsigned oUd = plane_at(P, PL_U + (coarsest ? 0u : (unsigned)(ucur ^ 1)));
+    const unsigned oUs = plane_at(P, PL_U + (unsigned)ucur);
+    const unsigned oPX = plane_at(P, PL_PX), oPY = plane_at(P, PL_PY);
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
@@ -153,16 +158,16 @@ __device__ __forceinline__ void op_level_init(const EngineParams& P, int level, 
         if (!coarsest) {
             int ya, yb; float b0, b1;
             lin_coeff_y(y, g.up_sy, cH, ya, yb, b0, b1);
-            const float2 s00 = Us[(unsigned)(ya * cW + x0)], s01 = Us[(unsigned)(ya * cW + x1)];
-            const float2 s10 = Us[(unsigned)(yb * cW + x0)], s11 = Us[(unsigned)(yb * cW + x1)];
+            const float2 s00 = SB[oUs + (unsigned)(ya * cW + x0)], s01 = SB[oUs + (unsigned)(ya * cW + x1)];
+            const float2 s10 = SB[oUs + (unsigned)(yb * cW + x0)], s11 = SB[oUs + (unsigned)(yb * cW + x1)];
             const float r0x = s00.x * a0 + s01.x * a1, r1x = s10.x * a0 + s11.x * a1;
             const float r0y = s00.y * a0 + s01.y * a1, r1y = s10.y * a0 + s11.y * a1;
             u.x = (r0x * b0 + r1x * b1) * P.up_mul;
             u.y = (r0y * b0 + r1y * b1) * P.up_mul;
         }
-        Ud[q] = u;
-        PXd[q] = make_float2(0.f, 0.f);
-        PYd[q] = make_float2(0.f, 0.f);
+        SB[oUd + q] = u;
+        SB[oPX + q] = make_float2(0.f, 0.f);
+        SB[oPY + q] = make_float2(0.f, 0.f);
     }
 }
 
@@ -170,9 +175,9 @@ __device__ __forceinline__ void op_level_init(const EngineParams& P, int level, 
 __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int ucur, int pair, int slot, int strip,
                                         int lane, const float4* s_cubic) {
     const LevelGeom& g = P.lv[level];
-    const size_t base = (size_t)slot * P.slot_px;
-    const float2* U = P.U[ucur] + base;
-    float4* COEF = P.COEF + base;
+    float2* SB = slot_base(P, slot);
+    const float2* U = SB + plane_at(P, PL_U + (unsigned)ucur);
+    float4* COEF = reinterpret_cast<float4*>(SB + plane_at(P, PL_COEF));
     const int fa = P.pair_a[pair], fb = P.pair_b[pair];
     const float* I0 = P.pyrI + (size_t)fa * P.frame_pyr_stride + g.pyr_off;
     const float4* G1 = P.pyrG + (size_t)fb * P.frame_pyr_stride + g.pyr_off;
@@ -197,9 +202,9 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
 // PH_MEDIAN: medianBlur(u1, ksize), medianBlur(u2, ksize) with BORDER_REPLICATE
 __device__ __forceinline__ void op_median(const EngineParams& P, int level, int ucur, int slot, int strip, int lane) {
     const LevelGeom& g = P.lv[level];
-    const size_t base = (size_t)slot * P.slot_px;
-    const float2* __restrict__ Us = P.U[ucur] + base;
-    float2* __restrict__ Ud = P.U[ucur ^ 1] + base;
+    float2* SB = slot_base(P, slot);
+    const float2* __restrict__ Us = SB + plane_at(P, PL_U + (unsigned)ucur);
+    float2* __restrict__ Ud = SB + plane_at(P, PL_U + (unsigned)(ucur ^ 1));
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
@@ -243,19 +248,6 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
 // ---- inner iteration pieces -------------------------------------------------------------------------------
 struct InnerRow { float2 u; float4 c; float2 px, py, pxl; };
 
-__device__ __forceinline__ InnerRow load_inner_row(const float2* __restrict__ U, const float4* __restrict__ COEF,
-                                                   const float2* __restrict__ PX, const float2* __restrict__ PY,
-                                                   unsigned q, bool lane0_has_left) {
-    InnerRow r;
-    r.u = __ldg(U + q);
-    r.c = __ldg(COEF + q);
-    r.px = __ldg(PX + q);
-    r.py = __ldg(PY + q);
-    r.pxl = make_float2(0.f, 0.f);
-    if (lane0_has_left) r.pxl = __ldg(PX + q - 1);   // only lane 0 of a strip that does not start at x = 0
-    return r;
-}
-
 // estimateV + divergence + estimateU for one pixel (tvl1flow.cpp order of operations), branch-free: the
 // thresholding division runs on every lane through the shared fast path and is selected where it applies.
 __device__ __forceinline__ float2 estimate_u_px(const InnerRow& r, float2 pxl, float2 pyu, bool x_is_0, bool y_is_0,
@@ -290,19 +282,14 @@ __device__ __forceinline__ float hypot_f(float a, float b) {
     return (float)sqrt((double)a * (double)a + (double)b * (double)b);
 }
 
-// PH_INNER: one primal-dual iteration, warp-autonomous register-rolling strip
+// PH_INNER: one primal-dual iteration, warp-autonomous register-rolling strip.
+// Addressing: one slot base pointer + seven 32-bit element indices that advance by W per row.
 __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int ucur, int pcur, int slot, int strip,
                                            int lane) {
     const LevelGeom& g = P.lv[level];
     const int W = g.W, H = g.H;
-    const size_t base = (size_t)slot * P.slot_px;
-    const float2* __restrict__ U = P.U[ucur] + base;
-    float2* __restrict__ Un = P.U[ucur ^ 1] + base;
-    const float2* __restrict__ PX = P.PX[pcur] + base;
-    const float2* __restrict__ PY = P.PY[pcur] + base;
-    float2* __restrict__ PXn = P.PX[pcur ^ 1] + base;
-    float2* __restrict__ PYn = P.PY[pcur ^ 1] + base;
-    const float4* __restrict__ COEF = P.COEF + base;
+    float2* __restrict__ SB = slot_base(P, slot);
+    const float4* __restrict__ SB4 = reinterpret_cast<const float4*>(SB);
     const float l_t = P.l_t, theta = P.theta, taut = P.taut;
 
     const int x0 = (strip % g.in_sx) * kIW;
@@ -314,20 +301,38 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     const bool x_is_0 = (x == 0);
     const bool lane0_left = (lane == 0 && x0 > 0);
     const int xc = valid ? x : W - 1;            // clamp: idle lanes read a legal address
-    unsigned q = (unsigned)(y0 * W + xc);   // pixel offset inside the slot plane (< 2^28)
+    const unsigned q0 = (unsigned)(y0 * W + xc); // pixel offset of the strip's first row
+    // element indices (float2 units; COEF in float4 units) of row y, advanced by W per row
+    unsigned iU = plane_at(P, PL_U + (unsigned)ucur) + q0, iUn = plane_at(P, PL_U + (unsigned)(ucur ^ 1)) + q0;
+    unsigned iPX = plane_at(P, PL_PX + (unsigned)pcur) + q0, iPXn = plane_at(P, PL_PX + (unsigned)(pcur ^ 1)) + q0;
+    unsigned iPY = plane_at(P, PL_PY + (unsigned)pcur) + q0, iPYn = plane_at(P, PL_PY + (unsigned)(pcur ^ 1)) + q0;
+    unsigned iC = (plane_at(P, PL_COEF) >> 1) + q0;
+    const unsigned uW = (unsigned)W;
+
+    auto load_row = [&](unsigned rows_ahead) {
+        const unsigned d = rows_ahead * uW;
+        InnerRow r;
+        r.u = __ldg(SB + iU + d);
+        r.c = __ldg(SB4 + iC + d);
+        r.px = __ldg(SB + iPX + d);
+        r.py = __ldg(SB + iPY + d);
+        r.pxl = make_float2(0.f, 0.f);
+        if (lane0_left) r.pxl = __ldg(SB + iPX + d - 1);   // only lane 0 of a strip that does not start at x = 0
+        return r;
+    };
 
     double err = 0.0;
     float2 pyu = make_float2(0.f, 0.f);
-    if (y0 > 0) pyu = __ldg(PY + q - W);
-    InnerRow cur = load_inner_row(U, COEF, PX, PY, q, lane0_left);
+    if (y0 > 0) pyu = __ldg(SB + iPY - uW);
+    InnerRow cur = load_row(0);
     InnerRow nxt = cur;
-    if (y0 + 1 < H) nxt = load_inner_row(U, COEF, PX, PY, q + W, lane0_left);
+    if (y0 + 1 < H) nxt = load_row(1);
 
     float2 pxl = make_float2(__shfl_up_sync(0xffffffffu, cur.px.x, 1), __shfl_up_sync(0xffffffffu, cur.px.y, 1));
     if (lane == 0) pxl = cur.pxl;
     float2 un = estimate_u_px(cur, pxl, pyu, x_is_0, y0 == 0, l_t, theta);
     if (owner) {
-        Un[q] = un;
+        SB[iUn] = un;
         const float t = (un.x - cur.u.x) * (un.x - cur.u.x) + (un.y - cur.u.y) * (un.y - cur.u.y);
         err += (double)t;
     }
@@ -338,13 +343,13 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         const bool has_next = (y + 1 < H);       // warp-uniform
         float2 un_n = make_float2(0.f, 0.f);
         InnerRow row = nxt;                      // row y+1 (already in flight)
-        if (y + 2 < H && y + 1 < y1) nxt = load_inner_row(U, COEF, PX, PY, q + 2u * (unsigned)W, lane0_left);
+        if (y + 2 < H && y + 1 < y1) nxt = load_row(2);
         if (has_next) {
             float2 pl = make_float2(__shfl_up_sync(0xffffffffu, row.px.x, 1), __shfl_up_sync(0xffffffffu, row.px.y, 1));
             if (lane == 0) pl = row.pxl;
             un_n = estimate_u_px(row, pl, py_c, x_is_0, false, l_t, theta);
             if (owner && y + 1 < y1) {
-                Un[q + W] = un_n;
+                SB[iUn + uW] = un_n;
                 const float t = (un_n.x - row.u.x) * (un_n.x - row.u.x) + (un_n.y - row.u.y) * (un_n.y - row.u.y);
                 err += (double)t;
             }
@@ -369,9 +374,9 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
             pxn.x = __fdiv_rn(a11, ng1); pyn.x = __fdiv_rn(a12, ng1);
             pxn.y = __fdiv_rn(a21, ng2); pyn.y = __fdiv_rn(a22, ng2);
         }
-        if (owner) { PXn[q] = pxn; PYn[q] = pyn; }
+        if (owner) { SB[iPXn] = pxn; SB[iPYn] = pyn; }
         un = un_n; px_c = row.px; py_c = row.py;
-        q += W;
+        iU += uW; iUn += uW; iPX += uW; iPXn += uW; iPY += uW; iPYn += uW; iC += uW;
     }
     // fixed-order warp reduction of the float64 error partial
 #pragma unroll
@@ -390,7 +395,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 __device__ __forceinline__ void op_wase(const EngineParams& P, int ucur, int slot, int strip, int lane, double& sum,
                                         double& cnt) {
     const LevelGeom& g = P.lv[0];
-    const float2* U = P.U[ucur] + (size_t)slot * P.slot_px;
+    const float2* U = slot_base(P, slot) + plane_at(P, PL_U + (unsigned)ucur);
     const float2* Wt = reinterpret_cast<const float2*>(P.wase_w);
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
@@ -416,8 +421,7 @@ __device__ __forceinline__ void op_wase(const EngineParams& P, int ucur, int slo
 __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pair, float bg, int slot, int strip,
                                          int lane) {
     const LevelGeom& g = P.lv[0];
-    const size_t base = (size_t)slot * P.slot_px;
-    const float2* U = P.U[ucur] + base;
+    const float2* U = slot_base(P, slot) + plane_at(P, PL_U + (unsigned)ucur);
     const size_t npx = (size_t)g.H * g.W;
     const int o0 = P.out_index[pair], o1 = P.dup_index[pair];
     const int x = (strip % g.pw_sx) * 32 + lane;
