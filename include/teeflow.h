@@ -132,6 +132,12 @@ TEEFLOW_API int teeflow_get_stats(teeflow_handle h, teeflow_stats* out);
 /* Pyramid geometry the handle would use for an H x W image: level sizes (finest first). Returns the level count. */
 TEEFLOW_API int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws);
 
+/* ---- frame prep: the `no_saliency=True` input stage, img2uint8(rgb2gray(frame)) per frame
+ * (calculate_optical_flow.py:588; optical_flow_utils.py:30-31).  rgb_dev: (n_frames,H,W,3) uint8, gray_dev:
+ * (n_frames,H,W) uint8, both device pointers. */
+TEEFLOW_API int teeflow_prepare_frames(teeflow_handle h, const uint8_t* rgb_dev, int n_frames, int H, int W,
+                                       uint8_t* gray_dev, void* stream);
+
 /* ---- WASE background compensation (calculate_optical_flow.py:649-660).
  * teeflow_wase_weights: w[y,x,c] = sum_n bkgd[n,y,x,c] from the (n_frames,H,W,2) bool mask `mask_dict['bkgd']`
  * (device pointers).  teeflow_set_wase(h, w_dev, H, W): every following calc_* subtracts, per pair, the scalar

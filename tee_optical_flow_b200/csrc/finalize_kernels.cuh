@@ -22,6 +22,47 @@ __global__ void wase_weights_kernel(const uint8_t* __restrict__ bkgd, int n_fram
     }
 }
 
+// ------------------------------------------------------------------------------------------------ frame prep
+// The `no_saliency=True` input stage of the pair loop (calculate_optical_flow.py:588): img2uint8(rgb2gray(frame))
+//   gray = R/255*0.2125 + G/255*0.7154 + B/255*0.0721 (float64, skimage.color.rgb2gray on img_as_float input)
+//   out  = img_as_ubyte((gray - min) / max) = clip(rint(((gray - min) / max) * 255))   (optical_flow_utils.py:30-31;
+//          sic: divides by the frame maximum, not by the range)
+__device__ __forceinline__ double rgb_to_gray(uchar3 p) {
+    const double r = (double)p.x / 255.0, g = (double)p.y / 255.0, b = (double)p.z / 255.0;
+    return (r * 0.2125 + g * 0.7154) + b * 0.0721;
+}
+__global__ void prep_minmax_kernel(const uint8_t* __restrict__ rgb, int npx, unsigned long long* __restrict__ mm /* [N][2] keys */) {
+    const int f = blockIdx.y;
+    const uint8_t* src = rgb + (size_t)f * npx * 3;
+    double mn = 1e300, mx = -1e300;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        const double g = rgb_to_gray(make_uchar3(src[3 * i], src[3 * i + 1], src[3 * i + 2]));
+        mn = fmin(mn, g); mx = fmax(mx, g);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, o));
+        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0 && mn <= mx) {
+        // gray >= 0: the IEEE bit pattern of a non-negative double is order-preserving as an unsigned integer
+        atomicMin(&mm[2 * f], (unsigned long long)__double_as_longlong(mn));
+        atomicMax(&mm[2 * f + 1], (unsigned long long)__double_as_longlong(mx));
+    }
+}
+__global__ void prep_quantize_kernel(const uint8_t* __restrict__ rgb, int npx, const unsigned long long* __restrict__ mm,
+                                     uint8_t* __restrict__ out) {
+    const int f = blockIdx.y;
+    const uint8_t* src = rgb + (size_t)f * npx * 3;
+    const double mn = __longlong_as_double((long long)mm[2 * f]), mx = __longlong_as_double((long long)mm[2 * f + 1]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        const double g = rgb_to_gray(make_uchar3(src[3 * i], src[3 * i + 1], src[3 * i + 2]));
+        double v = rint(((g - mn) / mx) * 255.0);
+        v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);      // NaN (all-black frame: 0/0) -> 0 like astype(uint8) of nan -> 0
+        out[(size_t)f * npx + i] = (uint8_t)(v == v ? v : 0.0);
+    }
+}
+
 // ------------------------------------------------------------------------------------- order-preserving keys
 __device__ __forceinline__ unsigned f32_key(float v) {
     const unsigned b = __float_as_uint(v);

@@ -53,6 +53,7 @@ struct teeflow_engine {
     unsigned* an_anghist = nullptr;
     long long* an_ranks = nullptr;
     unsigned long long* an_keys = nullptr;
+    unsigned long long* prep_mm = nullptr; size_t prep_cap = 0;
     void* an_edges = nullptr; unsigned long long* an_freq = nullptr; size_t an_freq_cap = 0;
     int* h_done = nullptr;     // pinned
     void* stage_in = nullptr; size_t stage_in_bytes = 0;
@@ -167,7 +168,7 @@ int teeflow_destroy(teeflow_handle h) {
     cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg);
     cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
     cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
-    cudaFree(h->an_edges); cudaFree(h->an_freq);
+    cudaFree(h->an_edges); cudaFree(h->an_freq); cudaFree(h->prep_mm);
     cudaFree(h->stage_in); cudaFree(h->stage_f32); cudaFree(h->stage_f16);
     cudaFreeHost(h->h_done);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -602,6 +603,28 @@ int teeflow_get_backgrounds(teeflow_handle h, float* bg_host, int n_pairs_cap) {
     CU_TRY(h, cudaSetDevice(h->device));
     if (n > 0) CU_TRY(h, cudaMemcpy(bg_host, h->bg, sizeof(float) * n, cudaMemcpyDeviceToHost));
     return n;
+}
+
+// ---- frame prep: img2uint8(rgb2gray(frame)) per frame (calculate_optical_flow.py:588, optical_flow_utils.py:30-31)
+int teeflow_prepare_frames(teeflow_handle h, const uint8_t* rgb_dev, int n_frames, int H, int W, uint8_t* gray_dev,
+                           void* stream_v) {
+    if (!h || !rgb_dev || !gray_dev || n_frames < 1 || H < 1 || W < 1) return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU_TRY(h, cudaSetDevice(h->device));
+    if ((size_t)n_frames * 2 > h->prep_cap) {
+        CU_TRY(h, regrow(h->prep_mm, (size_t)n_frames * 2));
+        h->prep_cap = (size_t)n_frames * 2;
+    }
+    std::vector<unsigned long long> init((size_t)n_frames * 2);
+    for (int f = 0; f < n_frames; ++f) { init[2 * f] = 0x7ff0000000000000ull; init[2 * f + 1] = 0ull; }   // +inf, +0
+    CU_TRY(h, cudaMemcpyAsync(h->prep_mm, init.data(), sizeof(unsigned long long) * init.size(), cudaMemcpyHostToDevice, stream));
+    const int npx = H * W;
+    const dim3 grid(std::max(1, std::min((npx + 256 * 4 - 1) / (256 * 4), 128)), n_frames);
+    prep_minmax_kernel<<<grid, 256, 0, stream>>>(rgb_dev, npx, h->prep_mm);
+    prep_quantize_kernel<<<grid, 256, 0, stream>>>(rgb_dev, npx, h->prep_mm, gray_dev);
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(stream));     // `init` is a host temporary
+    return TEEFLOW_OK;
 }
 
 // ---- masked radial / longitudinal decomposition + per-frame reductions (analysis.py, cardiac_cycle_detection.py)

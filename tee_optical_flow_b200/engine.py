@@ -251,6 +251,22 @@ class TVL1Engine:
         rs = lambda t: None if t is None else t.view(B, n_out, H, W, 2)
         return rs(f32), rs(f16)
 
+    # ------------------------------------------------------------------ frame prep
+    def prepare_frames(self, rgb):
+        """img2uint8(rgb2gray(frame)) per frame (calculate_optical_flow.py:588) on the GPU.  rgb: (N,H,W,3) uint8,
+        numpy -> numpy (N,H,W) uint8, CUDA torch tensor -> CUDA torch tensor."""
+        import torch
+        is_np = isinstance(rgb, np.ndarray)
+        t = torch.from_numpy(np.ascontiguousarray(rgb)) if is_np else rgb
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+            raise OpticalFlowCalculationError("rgb frames must be (N, H, W, 3) uint8")
+        t = t.to(torch.device("cuda", self.device)).contiguous()
+        N, H, W, _ = t.shape
+        out = torch.empty((N, H, W), dtype=torch.uint8, device=t.device)
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        self._check(self._lib.teeflow_prepare_frames(self._h, t.data_ptr(), N, H, W, out.data_ptr(), C.c_void_p(stream)))
+        return out.cpu().numpy() if is_np else out
+
     # ------------------------------------------------------------------ WASE background compensation
     def set_wase_masks(self, bkgd_mask) -> None:
         """bkgd_comp='WASE' (calculate_optical_flow.py:649-652): `bkgd_mask` is mask_dict['bkgd'], (N, H, W, 2) bool

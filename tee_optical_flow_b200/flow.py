@@ -33,8 +33,8 @@ def rgb2gray(rgb: np.ndarray) -> np.ndarray:
         a = a.astype(np.float64) / 255.0          # skimage img_as_float
     else:
         a = a.astype(np.float64)
-    coeffs = np.array([0.2125, 0.7154, 0.0721], dtype=np.float64)
-    return a @ coeffs
+    # explicit evaluation order (the GPU kernel uses the same): (R*c0 + G*c1) + B*c2, no BLAS
+    return (a[..., 0] * 0.2125 + a[..., 1] * 0.7154) + a[..., 2] * 0.0721
 
 
 def img2uint8(img: np.ndarray) -> np.ndarray:
@@ -114,15 +114,20 @@ def process_frames(frames: np.ndarray, mask_dict: Optional[Dict[str, np.ndarray]
     if bkgd_comp == 'WASE' and 'bkgd' not in mask_dict:
         raise ConfigurationError("bkgd_comp='WASE' needs mask_dict['bkgd']")
 
-    gray_u8 = frames if frames_are_prepared else prepare_frames(frames)
-    if gray_u8.dtype != np.uint8 or gray_u8.ndim != 3:
-        raise OpticalFlowCalculationError('prepared frames must be (N,H,W) uint8')
     conversion_factor = 1.0 if (pixel_spacing is None or frame_rate is None) else pixel_spacing * frame_rate   # :538-541
 
     own = engine is None
     if own:
         engine = TVL1Engine(**config.tvl1_params())
     try:
+        if frames_are_prepared:
+            gray_u8 = frames
+        elif frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[-1] == 3:
+            gray_u8 = engine.prepare_frames(frames)          # img2uint8(rgb2gray(.)) on the GPU (:588)
+        else:
+            gray_u8 = prepare_frames(frames)                 # unusual input dtypes: host formula
+        if gray_u8.dtype != np.uint8 or gray_u8.ndim != 3:
+            raise OpticalFlowCalculationError('prepared frames must be (N,H,W) uint8')
         engine.set_wase_masks(mask_dict['bkgd'] if bkgd_comp == 'WASE' else None)
         # pair loop (:584-597) + copy of the last flow (:599) + * conversion_factor (:600) + astype(float16) (:403)
         _, flow16 = engine.calc_clip(gray_u8, out_scale=conversion_factor, duplicate_last=True, want_f32=False,

@@ -181,3 +181,31 @@ def test_downstream_indices_identical(engine, clip, stored, ref, oracle):
     a = ref.radlong_peak_indices(rhi, rlo, sys_ref, nframes, **pk)
     b = ref.radlong_peak_indices(res["rad_hi"], res["rad_lo"], sys_gpu, nframes, **pk)
     assert a == b
+
+
+def test_frame_prep_matches_host_formula(engine):
+    """img2uint8(rgb2gray(frame)) (calculate_optical_flow.py:588, optical_flow_utils.py:30-31) on the GPU"""
+    from tee_optical_flow_b200.flow import prepare_frames
+    rng = np.random.default_rng(4)
+    rgb = rng.integers(0, 256, (5, 70, 90, 3), dtype=np.uint8)
+    rgb[1] = rgb[1] // 3 + 40                        # min > 0: the (sic) division by max, not by the range
+    rgb[2] = 0                                       # all-black frame
+    gray_rgb = np.repeat(rng.integers(0, 256, (1, 70, 90, 1), dtype=np.uint8), 3, axis=-1)
+    rgb[3] = gray_rgb[0]                             # gray2rgb input (R = G = B)
+    want = prepare_frames(rgb)
+    got = engine.prepare_frames(rgb)
+    assert got.dtype == np.uint8 and got.shape == (5, 70, 90)
+    with np.errstate(all="ignore"):
+        assert np.array_equal(got, want)
+
+
+def test_process_frames_rgb_input(engine, clip):
+    from tee_optical_flow_b200.flow import prepare_frames, process_frames
+    frames, masks = clip
+    rgb = np.stack([frames[:6]] * 3, axis=-1)
+    rgb[..., 1] = rgb[..., 1] // 2
+    out = process_frames(rgb, {k: v[:6] for k, v in masks.items()}, engine=engine)
+    gray = prepare_frames(rgb)
+    _, want = engine.calc_clip(gray, want_f32=False, want_f16=True)
+    assert np.array_equal(out['flow'], want)
+    assert out['attrs']['units_converted'] is False and out['echo'].shape == (6,) + frames.shape[1:]
