@@ -240,6 +240,32 @@ def main():
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
 
+    # ---- BASELINE config 3 (informational, outside the headline metric): masked radial / longitudinal
+    # decomposition + exact per-frame percentiles / angle mode of the stored fp16 flow, then (N > 1) the NCCL
+    # all-gather of the per-frame waveform rows -- the only exchange of the path
+    analysis = None
+    try:
+        from tee_optical_flow_b200.sharding import WAVEFORM_COLUMNS, gather_rows, pair_range
+        from tee_optical_flow_b200.synth import make_masks
+        nfr = N_FRAMES - 2
+        rv = torch.from_numpy(make_masks(rank, N_FRAMES, H, W)["rv"]).to(dev)
+        cent = np.tile(np.array([[0.77 * H, 0.5 * W]]), (nfr, 1))
+        eng.analyze_clip(out16, rv, cent, nfr)
+        barrier()
+        a0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            res = eng.analyze_clip(out16, rv, cent, nfr)
+            rows = np.stack([res[k] for k in WAVEFORM_COLUMNS[:6]], axis=1).astype(np.float64)
+            if world > 1:   # every rank contributes its clip's rows: gather of world * nfr rows
+                lo, hi = pair_range(world * nfr, rank, world)
+                gather_rows(rows[:hi - lo], world * nfr, rank, world, device=dev)
+        barrier()
+        analysis = {"ms_per_clip": 1e3 * (time.perf_counter() - a0) / reps, "frames": nfr,
+                    "what": "teeflow_analyze_clip (mag p99, angle mode, radial/longitudinal p1/p99) + waveform gather"}
+    except Exception as e:  # informational only
+        analysis = {"error": str(e)[:200]}
+
     t_max = torch.tensor([dev_s, wall_s, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
@@ -286,6 +312,7 @@ def main():
                          "launches_per_step": launches / args.steps,
                          "solver_share_of_step": solver_ms / 1e3 / step_s},
             "clocks": clocks,
+            "analysis_config3": analysis,
         }
         if world == 1 and not args.no_cpu_baseline:
             sample_pairs = 6
