@@ -445,7 +445,10 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
 }
 
 // ------------------------------------------------------------------------------------------- the super-step
-__global__ void __launch_bounds__(kThreads, 4)
+#ifndef TEEFLOW_MIN_CTAS
+#define TEEFLOW_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kThreads, TEEFLOW_MIN_CTAS)
 tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     __shared__ int s_prefix[kMaxSlots + 1];
     __shared__ float4 s_cubic[32];
