@@ -288,16 +288,20 @@ static cudaError_t regrow(T*& ptr, size_t count) {
 
 static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_stride, int S, size_t slot_px,
                             size_t max_tiles, size_t n_pairs) {
+    // a capacity is zeroed before its buffers are reallocated, so a failed cudaMalloc cannot leave a stale size
     if (n_frames * pyr_stride > h->cap_frames * h->cap_pyr_stride) {
+        h->cap_frames = 0; h->cap_pyr_stride = 0;
         CU_TRY(h, regrow(h->pyrI, n_frames * pyr_stride));
         CU_TRY(h, regrow(h->pyrG, n_frames * pyr_stride));
         h->cap_frames = n_frames; h->cap_pyr_stride = pyr_stride;
     }
     if ((size_t)S * slot_px > (size_t)h->cap_slots * h->cap_slot_px) {
+        h->cap_slots = 0; h->cap_slot_px = 0;
         CU_TRY(h, regrow(h->planes, (size_t)S * slot_px * kPlanes));
         h->cap_slots = S; h->cap_slot_px = slot_px;
     }
     if ((size_t)S * max_tiles > h->cap_tiles) {
+        h->cap_tiles = 0;
         CU_TRY(h, regrow(h->partial, (size_t)S * max_tiles));
         h->cap_tiles = (size_t)S * max_tiles;
     }
@@ -306,6 +310,7 @@ static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_strid
         CU_TRY(h, regrow(h->arrive, (size_t)kMaxSlots));
     }
     if (n_pairs > h->cap_pairs) {
+        h->cap_pairs = 0;
         CU_TRY(h, regrow(h->pair_lists, 4 * n_pairs));
         CU_TRY(h, regrow(h->counters, n_pairs * kMaxLevels * 3));
         CU_TRY(h, regrow(h->bg, n_pairs));

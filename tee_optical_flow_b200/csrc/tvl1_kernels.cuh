@@ -184,10 +184,14 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
+    // the flow / I0 of the next row are fetched while the current row's gather runs (one row ahead)
+    float2 u_n = __ldg(U + (unsigned)(y0 * g.W + x));
+    float i0_n = __ldg(I0 + (unsigned)(y0 * g.W + x));
     for (int y = y0; y < y1; ++y) {
         const unsigned q = (unsigned)(y * g.W + x);
-        const float2 u = U[q];
-        const float i0 = I0[q];
+        const float2 u = u_n;
+        const float i0 = i0_n;
+        if (y + 1 < y1) { u_n = __ldg(U + q + (unsigned)g.W); i0_n = __ldg(I0 + q + (unsigned)g.W); }
         const float mx = (float)x + u.x, my = (float)y + u.y;
         const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic);
         const float Ix2 = w.y * w.y, Iy2 = w.z * w.z;
