@@ -72,3 +72,24 @@ def test_downstream_restatements_selfcheck():
     assert y.shape == x.shape and np.abs(y - np.sin(np.linspace(0, 6 * np.pi, 60))).max() < 0.1
     with pytest.raises(ValueError):
         R.spectral_smooth(np.ones(10), 0.3, 20)
+
+
+def test_dataset_mirror_follows_reference_contract():
+    """optical_flow_dataset.py:45-111,172-229 on the in-memory HDF5 layout"""
+    from tee_optical_flow_b200.dataset import OpticalFlowDataset
+    rng = np.random.default_rng(2)
+    N, H, W = 7, 6, 8
+    flow = rng.standard_normal((N, H, W, 2)).astype(np.float16)
+    rv = rng.random((N, H, W, 1)) > 0.5
+    res = {'flow': flow, 'echo': np.zeros((N, H, W), np.float16), 'rv': np.repeat(rv, 2, axis=-1),
+           'attrs': {'nframes': N, 'mode': 'RVIO_2class', 'waveforms_present': False, 'units_converted': True,
+                     'frame_rate': 40.0, 'pixel_spacing': 0.05, 'ID': 'x', 'labels': ['rv']}}
+    ds = OpticalFlowDataset(res)
+    assert ds.nframes == N - 2 and ds.vel_array.dtype == np.float32
+    assert np.array_equal(ds.vel_array, flow.astype(np.float32))
+    assert np.array_equal(ds.accel_array, np.gradient(flow.astype(np.float32), 1 / 40.0, axis=0))
+    assert np.array_equal(ds.get_masked_arr('velocity', 'rv'), flow.astype(np.float32) * res['rv'])
+    assert np.array_equal(ds.get_masked_arr('PWR', 'rv'), ds.vel_array * ds.accel_array * res['rv'])
+    assert ds.get_masked_arr('velocity', 'nope') is None and ds.get_masked_arr('speed', 'rv') is None
+    res['attrs']['units_converted'] = False
+    assert OpticalFlowDataset(res).frame_rate == 1
