@@ -138,6 +138,21 @@ TEEFLOW_API int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs,
 TEEFLOW_API int teeflow_prepare_frames(teeflow_handle h, const uint8_t* rgb_dev, int n_frames, int H, int W,
                                        uint8_t* gray_dev, void* stream);
 
+/* ---- mask post-processing and AV centroid (connected components on the GPU)
+ * teeflow_clean_masks: the per-label pipeline of clean_mask (calculate_optical_flow.py:113-182) on a class map
+ * (n_frames,H,W) uint8 (SAM argmax): (class == class_id) -> moving_avg_mask(window, threshold) over frames (:91-111)
+ * -> scipy.ndimage.binary_fill_holes -> skimage remove_small_objects(min_size) per frame.  mask_dev: (n_frames,H,W)
+ * bool (0/1 bytes), device pointers.
+ * teeflow_av_centroids: calc_AV_centroid's per-frame step (analysis.py:58-63): 8-connected components of
+ * mask[..., 0] (mask_dev is (nframes,H,W,channels) bool), centroid (row, col) of the largest component (first in
+ * label order among ties); NaN when the frame is empty (the caller applies the copy-previous / image-centre
+ * fallback and the Savitzky-Golay filter). */
+TEEFLOW_API int teeflow_clean_masks(teeflow_handle h, const uint8_t* classmap_dev, int n_frames, int H, int W,
+                                    int class_id, int window, double threshold, int min_size, uint8_t* mask_dev,
+                                    void* stream);
+TEEFLOW_API int teeflow_av_centroids(teeflow_handle h, const uint8_t* mask_dev, int channels, int nframes, int H,
+                                     int W, double* centroids_host, int32_t* n_components_host, void* stream);
+
 /* ---- WASE background compensation (calculate_optical_flow.py:649-660).
  * teeflow_wase_weights: w[y,x,c] = sum_n bkgd[n,y,x,c] from the (n_frames,H,W,2) bool mask `mask_dict['bkgd']`
  * (device pointers).  teeflow_set_wase(h, w_dev, H, W): every following calc_* subtracts, per pair, the scalar

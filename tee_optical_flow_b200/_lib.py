@@ -69,6 +69,10 @@ SIGNATURES = {
     "teeflow_get_stats": (C.c_int, [C.c_void_p, C.POINTER(TeeflowStats)]),
     "teeflow_level_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p, _i32p]),
     "teeflow_prepare_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "teeflow_clean_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                      C.c_int, C.c_void_p, C.c_void_p]),
+    "teeflow_av_centroids": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p]),
     "teeflow_wase_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "teeflow_set_wase": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "teeflow_get_backgrounds": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),

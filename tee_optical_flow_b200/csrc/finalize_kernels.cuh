@@ -274,3 +274,135 @@ np_histogram_kernel(const T* __restrict__ vals, int npx, const T* __restrict__ e
 }
 
 }  // namespace teeflow
+
+// ============================================================================================================
+// Connected components (union-find with atomicMin) and the mask post-processing built on it
+// (calculate_optical_flow.py:91-182 clean_mask / moving_avg_mask; analysis.py:39-86 calc_AV_centroid).
+// Labels are the smallest pixel index of each component, i.e. components are ordered like skimage.measure.label /
+// scipy.ndimage.label (raster order of their first pixel).
+// ============================================================================================================
+namespace teeflow {
+
+// parents only ever decrease; reads are volatile because other threads hook roots concurrently
+__device__ __forceinline__ int uf_find(int* Lp, int i) {
+    volatile int* L = Lp;
+    int p = L[i];
+    while (p != i) {
+        const int gp = L[p];
+        if (gp != p) atomicMin(&Lp[i], gp);   // path halving; atomicMin keeps parents monotonically decreasing
+        i = p; p = gp;
+    }
+    return i;
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    for (;;) {
+        a = uf_find(L, a); b = uf_find(L, b);
+        if (a == b) return;
+        if (a > b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&L[b], a);     // hook the larger root under the smaller one
+        if (old == b) return;
+        b = old;
+    }
+}
+
+// moving_avg_mask (calculate_optical_flow.py:91-111): frames padded [first, 0..N-1, last, last]; window mean > thr
+__global__ void mask_vote_kernel(const uint8_t* __restrict__ cls, int N, int npx, int class_id, int window,
+                                 double threshold, uint8_t* __restrict__ out) {
+    const int f = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        int cnt = 0;
+        for (int k = 0; k < window; ++k) {
+            int t = f + k - 1;                                   // index into the un-padded sequence
+            t = t < 0 ? 0 : (t > N - 1 ? N - 1 : t);
+            cnt += cls[(size_t)t * npx + i] == class_id;
+        }
+        out[(size_t)f * npx + i] = ((double)cnt / (double)window) > threshold;
+    }
+}
+
+// L[i] = i for pixels whose value == fg, else -1.  img may be a multi-channel bool array (pixel stride `ch`).
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ img, int npx, int ch, int fg, int* __restrict__ L) {
+    const int f = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x)
+        L[(size_t)f * npx + i] = ((img[((size_t)f * npx + i) * ch] != 0) == (fg != 0)) ? i : -1;
+}
+__global__ void ccl_merge_kernel(int* Lall, int H, int W, int conn8) {
+    const int f = blockIdx.y;
+    int* L = Lall + (size_t)f * H * W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+        if (L[i] < 0) continue;
+        const int y = i / W, x = i - y * W;
+        if (x > 0 && L[i - 1] >= 0) uf_union(L, i, i - 1);
+        if (y > 0 && L[i - W] >= 0) uf_union(L, i, i - W);
+        if (conn8 && y > 0) {
+            if (x > 0 && L[i - W - 1] >= 0) uf_union(L, i, i - W - 1);
+            if (x < W - 1 && L[i - W + 1] >= 0) uf_union(L, i, i - W + 1);
+        }
+    }
+}
+// flatten + per-root statistics: area, (optionally) coordinate sums and border contact
+__global__ void ccl_stats_kernel(int* Lall, int H, int W, int* __restrict__ area,
+                                 unsigned long long* __restrict__ sum_r, unsigned long long* __restrict__ sum_c,
+                                 int* __restrict__ touches_border) {
+    const int f = blockIdx.y;
+    const size_t fo = (size_t)f * H * W;
+    int* L = Lall + fo;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+        if (L[i] < 0) continue;
+        const int r = uf_find(L, i);
+        L[i] = r;
+        atomicAdd(&area[fo + r], 1);
+        const int y = i / W, x = i - y * W;
+        if (sum_r) { atomicAdd(&sum_r[fo + r], (unsigned long long)y); atomicAdd(&sum_c[fo + r], (unsigned long long)x); }
+        if (touches_border && (y == 0 || x == 0 || y == H - 1 || x == W - 1)) touches_border[fo + r] = 1;
+    }
+}
+// binary_fill_holes: background components (4-connectivity) that do not touch the image border become foreground
+__global__ void fill_holes_kernel(uint8_t* __restrict__ m, const int* __restrict__ Lbg, const int* __restrict__ touches,
+                                  int npx) {
+    const int f = blockIdx.y;
+    const size_t fo = (size_t)f * npx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        const int r = Lbg[fo + i];
+        if (r >= 0 && !touches[fo + r]) m[fo + i] = 1;
+    }
+}
+// remove_small_objects(min_size): drop components with area < min_size
+__global__ void remove_small_kernel(uint8_t* __restrict__ m, const int* __restrict__ L, const int* __restrict__ area,
+                                    int npx, int min_size) {
+    const int f = blockIdx.y;
+    const size_t fo = (size_t)f * npx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        const int r = L[fo + i];
+        if (r >= 0 && area[fo + r] < min_size) m[fo + i] = 0;
+    }
+}
+// largest component per frame (first one in label order among ties): packed key (area << 32) | ~root, atomicMax
+__global__ void largest_component_kernel(const int* __restrict__ L, const int* __restrict__ area, int npx,
+                                         unsigned long long* __restrict__ best, int* __restrict__ n_comp) {
+    const int f = blockIdx.y;
+    const size_t fo = (size_t)f * npx;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+        if (L[fo + i] == i) {                       // a root
+            atomicAdd(&n_comp[f], 1);
+            const unsigned long long key = ((unsigned long long)(unsigned)area[fo + i] << 32) | (unsigned)(~(unsigned)i);
+            atomicMax(&best[f], key);
+        }
+    }
+}
+
+// (area, sum_r, sum_c) of each frame's winning root, so that the host reads one small array
+__global__ void largest_component_gather_kernel(const unsigned long long* __restrict__ best, const int* __restrict__ n_comp,
+                                                const unsigned long long* __restrict__ sum_r,
+                                                const unsigned long long* __restrict__ sum_c, int npx, int nf,
+                                                unsigned long long* __restrict__ out /* [nf][3] */) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    if (n_comp[f] == 0) { out[3 * f] = out[3 * f + 1] = out[3 * f + 2] = 0ull; return; }
+    const unsigned root = ~(unsigned)(best[f] & 0xffffffffull);
+    out[3 * f] = best[f] >> 32;
+    out[3 * f + 1] = sum_r[(size_t)f * npx + root];
+    out[3 * f + 2] = sum_c[(size_t)f * npx + root];
+}
+
+}  // namespace teeflow

@@ -54,6 +54,10 @@ struct teeflow_engine {
     long long* an_ranks = nullptr;
     unsigned long long* an_keys = nullptr;
     unsigned long long* prep_mm = nullptr; size_t prep_cap = 0;
+    // connected-component scratch (teeflow_clean_masks / teeflow_av_centroids), sized for kCclChunk frames
+    size_t ccl_cap = 0;
+    int *ccl_L = nullptr, *ccl_area = nullptr, *ccl_touch = nullptr, *ccl_ncomp = nullptr;
+    unsigned long long *ccl_sr = nullptr, *ccl_sc = nullptr, *ccl_best = nullptr;
     void* an_edges = nullptr; unsigned long long* an_freq = nullptr; size_t an_freq_cap = 0;
     int* h_done = nullptr;     // pinned
     void* stage_in = nullptr; size_t stage_in_bytes = 0;
@@ -169,6 +173,8 @@ int teeflow_destroy(teeflow_handle h) {
     cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
     cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
     cudaFree(h->an_edges); cudaFree(h->an_freq); cudaFree(h->prep_mm);
+    cudaFree(h->ccl_L); cudaFree(h->ccl_area); cudaFree(h->ccl_touch); cudaFree(h->ccl_ncomp);
+    cudaFree(h->ccl_sr); cudaFree(h->ccl_sc); cudaFree(h->ccl_best);
     cudaFree(h->stage_in); cudaFree(h->stage_f32); cudaFree(h->stage_f16);
     cudaFreeHost(h->h_done);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -629,6 +635,106 @@ int teeflow_prepare_frames(teeflow_handle h, const uint8_t* rgb_dev, int n_frame
     prep_quantize_kernel<<<grid, 256, 0, stream>>>(rgb_dev, npx, h->prep_mm, gray_dev);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(stream));     // `init` is a host temporary
+    return TEEFLOW_OK;
+}
+
+// ---- connected components: clean_mask (calculate_optical_flow.py:91-182) and calc_AV_centroid (analysis.py:39-86)
+static const int kCclChunk = 32;
+
+static int ccl_reserve(teeflow_engine* h, size_t npx) {
+    const size_t need = npx * kCclChunk;
+    if (need > h->ccl_cap) {
+        h->ccl_cap = 0;
+        CU_TRY(h, regrow(h->ccl_L, need)); CU_TRY(h, regrow(h->ccl_area, need)); CU_TRY(h, regrow(h->ccl_touch, need));
+        CU_TRY(h, regrow(h->ccl_sr, need)); CU_TRY(h, regrow(h->ccl_sc, need));
+        h->ccl_cap = need;
+    }
+    if (!h->ccl_best) { CU_TRY(h, regrow(h->ccl_best, (size_t)kCclChunk * 4)); CU_TRY(h, regrow(h->ccl_ncomp, (size_t)kCclChunk)); }
+    return TEEFLOW_OK;
+}
+
+// labels + per-root area (and optionally coordinate sums / border contact) of `nf` frames starting at img
+static int ccl_run(teeflow_engine* h, const uint8_t* img, int nf, int H, int W, int ch, int fg, int conn8, bool sums,
+                   bool border, cudaStream_t stream) {
+    const int npx = H * W;
+    const dim3 grid(std::max(1, std::min((npx + 255) / 256, 256)), nf);
+    ccl_init_kernel<<<grid, 256, 0, stream>>>(img, npx, ch, fg, h->ccl_L);
+    ccl_merge_kernel<<<grid, 256, 0, stream>>>(h->ccl_L, H, W, conn8);
+    CU_TRY(h, cudaMemsetAsync(h->ccl_area, 0, sizeof(int) * (size_t)nf * npx, stream));
+    if (sums) {
+        CU_TRY(h, cudaMemsetAsync(h->ccl_sr, 0, sizeof(unsigned long long) * (size_t)nf * npx, stream));
+        CU_TRY(h, cudaMemsetAsync(h->ccl_sc, 0, sizeof(unsigned long long) * (size_t)nf * npx, stream));
+    }
+    if (border) CU_TRY(h, cudaMemsetAsync(h->ccl_touch, 0, sizeof(int) * (size_t)nf * npx, stream));
+    ccl_stats_kernel<<<grid, 256, 0, stream>>>(h->ccl_L, H, W, h->ccl_area, sums ? h->ccl_sr : nullptr,
+                                               sums ? h->ccl_sc : nullptr, border ? h->ccl_touch : nullptr);
+    CU_TRY(h, cudaGetLastError());
+    return TEEFLOW_OK;
+}
+
+int teeflow_clean_masks(teeflow_handle h, const uint8_t* classmap_dev, int n_frames, int H, int W, int class_id,
+                        int window, double threshold, int min_size, uint8_t* mask_dev, void* stream_v) {
+    if (!h || !classmap_dev || !mask_dev || n_frames < 1 || H < 1 || W < 1 || window < 1)
+        return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int npx = H * W;
+    int rc = ccl_reserve(h, (size_t)npx);
+    if (rc) return rc;
+    const dim3 gall(std::max(1, std::min((npx + 255) / 256, 256)), n_frames);
+    mask_vote_kernel<<<gall, 256, 0, stream>>>(classmap_dev, n_frames, npx, class_id, window, threshold, mask_dev);
+    for (int f0 = 0; f0 < n_frames; f0 += kCclChunk) {
+        const int nf = std::min(kCclChunk, n_frames - f0);
+        uint8_t* m = mask_dev + (size_t)f0 * npx;
+        const dim3 grid(gall.x, nf);
+        // binary_fill_holes: 4-connected background components that do not reach the image border
+        if ((rc = ccl_run(h, m, nf, H, W, 1, /*fg=*/0, /*conn8=*/0, false, true, stream))) return rc;
+        fill_holes_kernel<<<grid, 256, 0, stream>>>(m, h->ccl_L, h->ccl_touch, npx);
+        // remove_small_objects(min_size), connectivity 1
+        if ((rc = ccl_run(h, m, nf, H, W, 1, /*fg=*/1, /*conn8=*/0, false, false, stream))) return rc;
+        remove_small_kernel<<<grid, 256, 0, stream>>>(m, h->ccl_L, h->ccl_area, npx, min_size);
+    }
+    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, cudaStreamSynchronize(stream));
+    return TEEFLOW_OK;
+}
+
+int teeflow_av_centroids(teeflow_handle h, const uint8_t* mask_dev, int channels, int nframes, int H, int W,
+                         double* centroids_host, int32_t* n_components_host, void* stream_v) {
+    if (!h || !mask_dev || !centroids_host || nframes < 1 || H < 1 || W < 1 || channels < 1)
+        return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int npx = H * W;
+    int rc = ccl_reserve(h, (size_t)npx);
+    if (rc) return rc;
+    std::vector<unsigned long long> best((size_t)kCclChunk * 3);
+    std::vector<int> ncomp(kCclChunk);
+    for (int f0 = 0; f0 < nframes; f0 += kCclChunk) {
+        const int nf = std::min(kCclChunk, nframes - f0);
+        const uint8_t* m = mask_dev + (size_t)f0 * npx * channels;
+        // skimage.measure.label default connectivity for 2-D = 2 (8-connected); channel 0 of the mask (analysis.py:59)
+        if ((rc = ccl_run(h, m, nf, H, W, channels, 1, 1, true, false, stream))) return rc;
+        CU_TRY(h, cudaMemsetAsync(h->ccl_best, 0, sizeof(unsigned long long) * nf, stream));
+        CU_TRY(h, cudaMemsetAsync(h->ccl_ncomp, 0, sizeof(int) * nf, stream));
+        const dim3 grid(std::max(1, std::min((npx + 255) / 256, 256)), nf);
+        largest_component_kernel<<<grid, 256, 0, stream>>>(h->ccl_L, h->ccl_area, npx, h->ccl_best, h->ccl_ncomp);
+        CU_TRY(h, cudaGetLastError());
+        largest_component_gather_kernel<<<1, kCclChunk, 0, stream>>>(h->ccl_best, h->ccl_ncomp, h->ccl_sr, h->ccl_sc, npx,
+                                                                     nf, h->ccl_best + kCclChunk);
+        CU_TRY(h, cudaGetLastError());
+        CU_TRY(h, cudaMemcpyAsync(best.data(), h->ccl_best + kCclChunk, sizeof(unsigned long long) * 3 * nf,
+                                  cudaMemcpyDeviceToHost, stream));
+        CU_TRY(h, cudaMemcpyAsync(ncomp.data(), h->ccl_ncomp, sizeof(int) * nf, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(h, cudaStreamSynchronize(stream));
+        for (int f = 0; f < nf; ++f) {
+            if (n_components_host) n_components_host[f0 + f] = ncomp[f];
+            if (ncomp[f] == 0) { centroids_host[2 * (f0 + f)] = centroids_host[2 * (f0 + f) + 1] = std::nan(""); continue; }
+            const double area = (double)best[3 * f];
+            centroids_host[2 * (f0 + f)] = (double)best[3 * f + 1] / area;      // regionprops.centroid: mean (row, col)
+            centroids_host[2 * (f0 + f) + 1] = (double)best[3 * f + 2] / area;
+        }
+    }
     return TEEFLOW_OK;
 }
 

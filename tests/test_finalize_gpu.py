@@ -209,3 +209,51 @@ def test_process_frames_rgb_input(engine, clip):
     _, want = engine.calc_clip(gray, want_f32=False, want_f16=True)
     assert np.array_equal(out['flow'], want)
     assert out['attrs']['units_converted'] is False and out['echo'].shape == (6,) + frames.shape[1:]
+
+
+def _class_map(seed, N, H, W):
+    """noisy SAM-like argmax map: two classes with holes, specks and frame-to-frame flicker"""
+    from tee_optical_flow_b200.synth import make_masks
+    rng = np.random.default_rng(seed)
+    m = make_masks(seed, N, H, W, period=9.0)
+    cm = np.zeros((N, H, W), np.uint8)
+    cm[m["rv"][..., 0]] = 1
+    cm[m["av"][..., 0]] = 2
+    flick = rng.random((N, H, W))
+    cm[flick < 0.04] = 0                                   # holes / drop-outs
+    cm[(flick > 0.985) & (cm == 0)] = 1                    # specks
+    cm[(flick > 0.97) & (flick <= 0.985) & (cm == 0)] = 2
+    cm[3, 10:40, 10:60] = 1                                # a blob present in a single frame (voted away)
+    cm[5:9, 60:75, 5:25] = 2                               # a second AV component, smaller than the main one
+    return cm
+
+
+def test_clean_mask_matches_reference(engine, ref):
+    """clean_mask (calculate_optical_flow.py:113-182): temporal vote, binary_fill_holes, remove_small_objects, bkgd"""
+    from tee_optical_flow_b200.config import OpticalFlowCalculationConfig
+    from tee_optical_flow_b200.masks import MODE_CLASSES, clean_mask
+    cm = _class_map(11, 14, 90, 120)
+    cfg = OpticalFlowCalculationConfig(min_mask_size=60)
+    got = clean_mask(engine, cm, mode='RVIO_2class', config=cfg)
+    want = ref.clean_mask(cm, MODE_CLASSES['RVIO_2class'], min_size=60)
+    assert set(got) == {'rv', 'av', 'bkgd'}
+    for k in want:
+        assert got[k].shape == want[k].shape == (14, 90, 120, 2) and got[k].dtype == bool
+        assert np.array_equal(got[k], want[k]), k
+    assert clean_mask(engine, cm, mode='nope') is None
+    assert want['rv'][3, 20, 30, 0] == False and got['rv'].any()
+
+
+def test_av_centroid_matches_reference(engine, ref):
+    """calc_AV_centroid (analysis.py:39-86): largest 8-connected component, fallbacks, Savitzky-Golay"""
+    from tee_optical_flow_b200.masks import MODE_CLASSES, calc_AV_centroid
+    cm = _class_map(12, 16, 90, 120)
+    masks = ref.clean_mask(cm, MODE_CLASSES['RVIO_2class'], min_size=30)
+    av = masks['av'].copy()
+    av[0] = False                                          # first frame empty -> image centre
+    av[7] = False                                          # empty in the middle -> copy previous
+    for filt in (False, True):
+        got = np.asarray(calc_AV_centroid(engine, av, 14, filter=filt))
+        want = ref.calc_av_centroid(av, 14, do_filter=filt)
+        assert got.shape == (14, 2)
+        assert np.array_equal(got, np.asarray(want)), filt
