@@ -385,7 +385,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     for (int i = 0; i < 2; ++i) P.slots[i] = h->slots + (size_t)i * kMaxSlots;
     P.planes = h->planes; P.slot_stride = (long long)kPlanes * P.slot_px;
     P.arrive = h->arrive; P.partial = h->partial;
-    P.next_pair = h->ctl; P.pairs_done = h->ctl + 1;
+    P.next_pair = h->ctl; P.pairs_done = h->ctl + 1; P.item_counter = h->ctl + 2;
     P.pair_a = h->pair_lists; P.pair_b = h->pair_lists + h->cap_pairs;
     P.out_index = h->pair_lists + 2 * h->cap_pairs; P.dup_index = h->pair_lists + 3 * h->cap_pairs;
     P.counters_out = h->counters;

@@ -20,6 +20,9 @@ constexpr int kWarpsPerCta = kThreads / 32;
 constexpr int kIW = 31;        // inner strip: output columns per warp (lane 31 = right halo column)
 constexpr int kIR = 32;        // inner strip: rows per warp
 constexpr int kPR = 8;         // pointwise strip: rows per warp (32 columns)
+#ifndef TEEFLOW_DYNAMIC_ITEMS
+#define TEEFLOW_DYNAMIC_ITEMS 1
+#endif
 
 // ------------------------------------------------------------------------------------------------ pyramid
 // level 0: convertTo(CV_32F, 1) for u8, x255 for f32 (tvl1flow.cpp: I0mult / I1mult)
@@ -476,9 +479,20 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
         for (int s = tid; s < P.S; s += kThreads)
             if (s_prefix[s + 1] == s_prefix[s]) nxt[s] = cur[s];
 
+#if TEEFLOW_DYNAMIC_ITEMS
+    // dynamic distribution: every warp pulls the next strip from a per-launch counter, so strips of unequal cost
+    // (inner / median / warp phases mix in one launch) balance out; the counter of the other parity is re-armed
+    if (blockIdx.x == 0 && tid == 0) P.item_counter[parity ^ 1] = 0;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(P.item_counter + parity, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+#else
     const int n_warps = gridDim.x * kWarpsPerCta;
     // CTA-interleaved item order: the 8 warps of a CTA take 8 consecutive strips (shared cache lines)
     for (int item = blockIdx.x * kWarpsPerCta + (tid >> 5); item < total; item += n_warps) {
+#endif
         int lo = 0, hi = P.S;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] <= item) lo = mid; else hi = mid; }
         const int slot = lo;
