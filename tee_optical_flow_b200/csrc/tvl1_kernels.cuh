@@ -18,7 +18,7 @@ namespace teeflow {
 constexpr int kThreads = 256;  // threads per CTA
 constexpr int kWarpsPerCta = kThreads / 32;
 constexpr int kIW = 31;        // inner strip: output columns per warp (lane 31 = right halo column)
-constexpr int kIR = 32;        // inner strip: rows per warp
+constexpr int kIR = 16;        // inner strip: rows per warp (16 beats 32 / 24 / 12 / 8 once strips are handed out dynamically)
 constexpr int kPR = 8;         // pointwise strip: rows per warp (32 columns)
 #ifndef TEEFLOW_DYNAMIC_ITEMS
 #define TEEFLOW_DYNAMIC_ITEMS 1
