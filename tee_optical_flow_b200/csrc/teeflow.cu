@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -22,6 +23,9 @@ using namespace teeflow;
 static_assert(TEEFLOW_MAX_LEVELS == kMaxLevels, "ABI level count");
 
 static thread_local std::string g_last_error;
+static const int kMaxGroups = 4;        // slot groups (streams) per handle
+static const int kMinGroupSlots = 4;    // do not split fewer than 2 * this many slots
+static const int kCtlInts = 2 + 2 * kMaxGroups;   // next_pair, pairs_done, per-group item counters [parity]
 
 struct teeflow_engine {
     teeflow_params p;
@@ -66,6 +70,9 @@ struct teeflow_engine {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_tp = nullptr;
     cudaStream_t own_stream = nullptr;
+    int groups = 2;                                   // slot groups stepping on separate streams
+    cudaStream_t group_stream[kMaxGroups - 1] = {};
+    cudaEvent_t ev_group[2][kMaxGroups - 1] = {};
     // last-call record
     teeflow_stats st{};
 };
@@ -154,12 +161,17 @@ int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
     if (occ < 1) { delete h; return fail(nullptr, TEEFLOW_ERR_CUDA, "tvl1_step_kernel cannot be resident on this device"); }
     h->ctas_per_sm = occ;
     CU_TRY(h, cudaMallocHost(&h->h_done, sizeof(int) * 4));
-    CU_TRY(h, cudaMalloc(&h->ctl, sizeof(int) * 4));
+    CU_TRY(h, cudaMalloc(&h->ctl, sizeof(int) * kCtlInts));
     for (auto& ev : h->ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU_TRY(h, cudaEventCreate(&h->ev_t0));
     CU_TRY(h, cudaEventCreate(&h->ev_t1));
     CU_TRY(h, cudaEventCreate(&h->ev_tp));
     CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    for (int g = 0; g < kMaxGroups - 1; ++g) {
+        CU_TRY(h, cudaStreamCreateWithFlags(&h->group_stream[g], cudaStreamNonBlocking));
+        for (int w = 0; w < 2; ++w) CU_TRY(h, cudaEventCreateWithFlags(&h->ev_group[w][g], cudaEventDisableTiming));
+    }
+    if (const char* e = getenv("TEEFLOW_GROUPS")) h->groups = std::max(1, std::min(atoi(e), kMaxGroups));
     *out = h;
     return TEEFLOW_OK;
 }
@@ -182,6 +194,10 @@ int teeflow_destroy(teeflow_handle h) {
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->ev_tp) cudaEventDestroy(h->ev_tp);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int g = 0; g < kMaxGroups - 1; ++g) {
+        if (h->group_stream[g]) cudaStreamDestroy(h->group_stream[g]);
+        for (int w = 0; w < 2; ++w) if (h->ev_group[w][g]) cudaEventDestroy(h->ev_group[w][g]);
+    }
     delete h;
     return TEEFLOW_OK;
 }
@@ -434,47 +450,69 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         }
         CU_TRY(h, cudaMemcpyAsync(h->slots, init.data(), sizeof(Slot) * kMaxSlots, cudaMemcpyHostToDevice, stream));
         CU_TRY(h, cudaMemsetAsync(h->arrive, 0, sizeof(unsigned) * kMaxSlots, stream));
-        const int ctl0[4] = {S, 0, 0, 0};
+        int ctl0[kCtlInts] = {0};
+        ctl0[0] = S;
         CU_TRY(h, cudaMemcpyAsync(h->ctl, ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, stream));
         CU_TRY(h, cudaStreamSynchronize(stream));  // `init` / ctl0 / pair lists are host temporaries
         CU_TRY(h, cudaEventRecord(h->ev_tp, stream));
     }
 
-    // ---- super-steps.  The host keeps two chunks of launches in flight and polls the done counter of the
-    // chunk before; finished slots make their CTAs exit at once, so an over-issued launch costs microseconds.
+    // ---- super-steps.  The slots are split into groups that step on separate streams: while one group's launch
+    // drains (its last strips, the launch gap, the next launch's prologue) the other group's strips keep the SMs
+    // busy.  The host keeps two chunks of launches in flight per stream and polls the done counter of the chunk
+    // before; finished slots make their warps exit at once, so an over-issued launch costs microseconds.
     const int grid = h->num_sms * h->ctas_per_sm;
     const int chunk = 16;
-    // upper bound on steps per pair: per level 1 init + warps * (1 + outer * (1 + inner)), + 1 final
+    const int G = (S >= 2 * kMinGroupSlots && h->groups > 1) ? std::min(h->groups, kMaxGroups) : 1;
+    EngineParams Pg[kMaxGroups];
+    cudaStream_t gs[kMaxGroups];
+    for (int g = 0; g < G; ++g) {
+        Pg[g] = P;
+        Pg[g].slot0 = (int)((long long)S * g / G);
+        Pg[g].S = (int)((long long)S * (g + 1) / G) - Pg[g].slot0;
+        Pg[g].item_counter = h->ctl + 2 + 2 * g;
+        gs[g] = g == 0 ? stream : h->group_stream[g - 1];
+        if (g > 0) CU_TRY(h, cudaStreamWaitEvent(gs[g], h->ev_tp, 0));      // pyramid + slot table are ready
+    }
+    // upper bound on steps per pair: per level 1 init + warps * (1 + outer * (1 + inner)), + wase + final
     const long long steps_per_pair = (long long)L * (1 + (long long)h->p.warps * (1 + (long long)h->p.outer_iterations * (1 + h->p.inner_iterations))) + 2;
-    const long long max_steps = steps_per_pair * ((n_pairs + S - 1) / S + 1) + 2 * chunk;
+    const long long max_steps = steps_per_pair * ((n_pairs + S - 1) / S + 1) * G + 2 * chunk;
     long long step = 0;
-    int pending = 0;  // chunks whose done-counter copy has been issued but not yet checked
+    int n_chunks = 0;
     bool done = false;
     volatile int* hd = h->h_done;
     hd[0] = hd[1] = 0;
     while (!done) {
         if (step > max_steps) return fail(h, TEEFLOW_ERR_STATE, "scheduler exceeded %lld steps", max_steps);
         for (int k = 0; k < chunk; ++k, ++step)
-            tvl1_step_kernel<<<grid, kThreads, 0, stream>>>(P, (int)(step & 1));
+            for (int g = 0; g < G; ++g)
+                tvl1_step_kernel<<<grid, kThreads, 0, gs[g]>>>(Pg[g], (int)(step & 1));
         CU_TRY(h, cudaGetLastError());
-        const int which = (int)((step / chunk) & 1);
+        const int which = n_chunks & 1;
+        // join the group streams into the caller's stream at the chunk boundary, then sample the done counter
+        for (int g = 1; g < G; ++g) {
+            CU_TRY(h, cudaEventRecord(h->ev_group[which][g - 1], gs[g]));
+            CU_TRY(h, cudaStreamWaitEvent(stream, h->ev_group[which][g - 1], 0));
+        }
         CU_TRY(h, cudaMemcpyAsync((void*)(hd + which), h->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CU_TRY(h, cudaEventRecord(h->ev[which], stream));
-        if (++pending == 2) {
+        for (int g = 1; g < G; ++g) CU_TRY(h, cudaStreamWaitEvent(gs[g], h->ev[which], 0));
+        if (++n_chunks >= 2) {
             const int prev = which ^ 1;
             CU_TRY(h, cudaEventSynchronize(h->ev[prev]));
-            --pending;
             if (hd[prev] >= n_pairs) done = true;
         }
     }
     CU_TRY(h, cudaEventRecord(h->ev_t1, stream));
     CU_TRY(h, cudaStreamSynchronize(stream));
+    for (int g = 1; g < G; ++g) CU_TRY(h, cudaStreamSynchronize(gs[g]));
     if (hd[0] < n_pairs && hd[1] < n_pairs) {
         // the last issued chunk may be the one that finished the work
         int d = 0;
         CU_TRY(h, cudaMemcpy(&d, h->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost));
         if (d < n_pairs) return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", d, n_pairs);
     }
+    step *= G;
     CU_TRY(h, cudaEventElapsedTime(&h->st.device_ms, h->ev_t0, h->ev_t1));
     CU_TRY(h, cudaEventElapsedTime(&h->st.pyramid_ms, h->ev_t0, h->ev_tp));
     CU_TRY(h, cudaEventElapsedTime(&h->st.solver_ms, h->ev_tp, h->ev_t1));

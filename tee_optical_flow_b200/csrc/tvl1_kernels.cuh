@@ -460,8 +460,10 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     __shared__ int s_prefix[kMaxSlots + 1];
     __shared__ float4 s_cubic[32];
 
-    const Slot* __restrict__ cur = P.slots[parity];
-    Slot* __restrict__ nxt = P.slots[parity ^ 1];
+    // this launch serves the slot group [slot0, slot0 + S): groups run on separate streams so that the tail and
+    // the launch gap of one group's step are filled by the other group's strips
+    const Slot* __restrict__ cur = P.slots[parity] + P.slot0;
+    Slot* __restrict__ nxt = P.slots[parity ^ 1] + P.slot0;
     const int tid = threadIdx.x, lane = tid & 31;
 
     if (tid < 32) s_cubic[tid] = cubic_coeffs(tid);
@@ -495,11 +497,11 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
 #endif
         int lo = 0, hi = P.S;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] <= item) lo = mid; else hi = mid; }
-        const int slot = lo;
-        const int strip = item - s_prefix[slot];
-        const Slot* sp = cur + slot;
+        const int slot = P.slot0 + lo;            // absolute slot: planes, arrival counter, partials
+        const int strip = item - s_prefix[lo];
+        const Slot* sp = cur + lo;
         const int pair = sp->pair, phase = sp->phase, level = sp->level, ucur = sp->ucur, pcur = sp->pcur;
-        const int n_items = s_prefix[slot + 1] - s_prefix[slot];
+        const int n_items = s_prefix[lo + 1] - s_prefix[lo];
 
         double err = 0.0, aux = 0.0;
         switch (phase) {
@@ -559,7 +561,7 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
                 } else {
                     advance_slot(P, n, e);
                 }
-                nxt[slot] = n;
+                nxt[lo] = n;
                 P.arrive[slot] = 0u;
             }
         }
