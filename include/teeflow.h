@@ -196,6 +196,13 @@ TEEFLOW_API int teeflow_analysis_histogram(teeflow_handle h, int quantity, const
  * pseudo-random operand pairs (mode 0: dual-update operand ranges, 1: thresholding ranges, 2: all exponents) and
  * returns the number of bit mismatches (must be 0). */
 TEEFLOW_API int teeflow_selftest_division(teeflow_handle h, int mode, int64_t n, uint64_t seed, int64_t* mismatches);
+/* Diagnostics: compares the inner iteration's packed float-float hypot (fast form) with
+ * (float)sqrt((double)a*a + (double)b*b) on n pseudo-random operand pairs (mode 0: flow-gradient magnitudes
+ * 2^-30..2^4, both operands of similar size; 1: very different magnitudes, zeros and exact squares mixed in;
+ * 2: all exponents incl. denormals / huge).  mismatches = pairs the fast form ACCEPTED with a wrong result (must
+ * be 0); rejected = pairs it handed to the exact form. */
+TEEFLOW_API int teeflow_selftest_hypot(teeflow_handle h, int mode, int64_t n, uint64_t seed, int64_t* mismatches,
+                                       int64_t* rejected);
 
 #ifdef __cplusplus
 }

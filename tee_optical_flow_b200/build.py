@@ -46,7 +46,9 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *map(str, SOURCES)]
+    # TEEFLOW_NVCC_EXTRA: extra flags for tuning experiments (e.g. "-DTEEFLOW_MIN_CTAS=3 -DTEEFLOW_RING=2")
+    extra = os.environ.get("TEEFLOW_NVCC_EXTRA", "").split()
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", str(LIB), *map(str, SOURCES)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

@@ -26,20 +26,36 @@ static thread_local std::string g_last_error;
 static const int kMaxGroups = 4;        // slot groups (streams) per handle
 static const int kMinGroupSlots = 4;    // do not split fewer than 2 * this many slots
 static const int kCtlInts = 2 + 2 * kMaxGroups;   // next_pair, pairs_done, per-group item counters [parity]
+#ifndef TEEFLOW_PITCH0
+#define TEEFLOW_PITCH0 1024
+#endif
+static const int kPitches[] = {TEEFLOW_PITCH0, 2048, 4096};  // instantiated plane pitches (float2 elements): W <= pitch
+static const size_t kPlaneAlign = (size_t)kPlanes * 4096 * sizeof(float2);   // Lay<4096>::ROWB, a multiple of the others
+
+typedef void (*step_kernel_t)(const EngineParams, const int);
+static step_kernel_t step_kernel_for(int pitch) {
+    switch (pitch) {
+        case TEEFLOW_PITCH0: return tvl1_step_kernel<TEEFLOW_PITCH0>;
+        case 2048: return tvl1_step_kernel<2048>;
+        case 4096: return tvl1_step_kernel<4096>;
+        default: return nullptr;
+    }
+}
 
 struct teeflow_engine {
     teeflow_params p;
     int device = 0;
     int num_sms = 0;
-    int ctas_per_sm = 1;
+    int ctas_per_sm[3] = {1, 1, 1};   // per instantiated pitch
     std::string err;
     // workspace (grown on demand)
     size_t cap_frames = 0, cap_pyr_stride = 0;
-    int cap_slots = 0;
-    size_t cap_slot_px = 0, cap_tiles = 0, cap_pairs = 0;
+    size_t cap_plane_elems = 0;   // float2 elements available behind `planes`
+    size_t cap_tiles = 0, cap_pairs = 0;
     float* pyrI = nullptr;
     float4* pyrG = nullptr;
-    float2* planes = nullptr;  // [S][kPlanes][slot_px]
+    void* planes_raw = nullptr;   // allocation behind `planes`
+    float2* planes = nullptr;     // [S][H0][kPlanes][PITCH], aligned to kPlaneAlign (struct Lay)
     Slot* slots = nullptr;     // [2][S]
     unsigned* arrive = nullptr;
     double* partial = nullptr;
@@ -156,10 +172,12 @@ int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
     cudaDeviceProp prop;
     CU_TRY(h, cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
-    int occ = 0;
-    CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tvl1_step_kernel, kThreads, 0));
-    if (occ < 1) { delete h; return fail(nullptr, TEEFLOW_ERR_CUDA, "tvl1_step_kernel cannot be resident on this device"); }
-    h->ctas_per_sm = occ;
+    for (int i = 0; i < 3; ++i) {
+        int occ = 0;
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_for(kPitches[i]), kThreads, 0));
+        if (occ < 1) { delete h; return fail(nullptr, TEEFLOW_ERR_CUDA, "tvl1_step_kernel cannot be resident on this device"); }
+        h->ctas_per_sm[i] = occ;
+    }
     CU_TRY(h, cudaMallocHost(&h->h_done, sizeof(int) * 4));
     CU_TRY(h, cudaMalloc(&h->ctl, sizeof(int) * kCtlInts));
     for (auto& ev : h->ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -180,7 +198,7 @@ int teeflow_destroy(teeflow_handle h) {
     if (!h) return TEEFLOW_OK;
     cudaSetDevice(h->device);
     cudaFree(h->pyrI); cudaFree(h->pyrG);
-    cudaFree(h->planes); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
+    cudaFree(h->planes_raw); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
     cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg);
     cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
     cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
@@ -301,6 +319,61 @@ extern "C" TEEFLOW_API int teeflow_selftest_division(teeflow_handle h, int mode,
     return TEEFLOW_OK;
 }
 
+// ---- self test of the packed float-float hypot (fast form of the dual update)
+__global__ void selftest_hypot_kernel(unsigned long long n, unsigned long long seed, int mode, float negzero,
+                                      unsigned long long* out) {
+    unsigned long long bad = 0, rej = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        float v[4];
+        for (int k = 0; k < 2; ++k) {     // two operand pairs per call: the fast form works on both channels at once
+            unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (2 * i + k + 1);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+            const unsigned ma = (unsigned)z & 0x7FFFFFu, mb = (unsigned)(z >> 23) & 0x7FFFFFu;
+            const unsigned sa = (unsigned)(z >> 46) & 1u, sb = (unsigned)(z >> 47) & 1u;
+            int ea, eb;
+            if (mode == 0) { ea = 127 - 30 + (int)((z >> 48) % 35); eb = ea - 3 + (int)((z >> 56) % 7); }
+            else if (mode == 1) { ea = 127 - 40 + (int)((z >> 48) % 60); eb = 127 - 60 + (int)((z >> 56) % 80); }
+            else { ea = (int)((z >> 48) % 255); eb = (int)((z >> 56) % 255); }
+            float a = __uint_as_float((sa << 31) | ((unsigned)ea << 23) | ma);
+            float b = __uint_as_float((sb << 31) | ((unsigned)eb << 23) | mb);
+            if (mode == 1) {
+                const unsigned sel = (unsigned)(z >> 60) & 7u;
+                if (sel == 0) a = 0.0f;
+                if (sel == 1) b = -0.0f;
+                if (sel == 2) { a = 0.0f; b = 0.0f; }
+                if (sel == 3) { a = (float)(int)(ma >> 12); b = 0.0f; }                            // exact results
+                if (sel == 4) { a = 3.0f * (float)(1 + (ma >> 14)); b = 4.0f * (float)(1 + (ma >> 14)); }  // 3-4-5
+            }
+            v[2 * k] = a; v[2 * k + 1] = b;
+        }
+        bool ok;
+        const float2 g = hypot2_fast(make_float2(v[0], v[2]), make_float2(v[1], v[3]), negzero, ok);
+        if (!ok) { ++rej; continue; }
+        const float w0 = hypot_f(v[0], v[1]), w1 = hypot_f(v[2], v[3]);
+        bad += (__float_as_uint(g.x) != __float_as_uint(w0)) || (__float_as_uint(g.y) != __float_as_uint(w1));
+    }
+    if (bad) atomicAdd(out, bad);
+    if (rej) atomicAdd(out + 1, rej);
+}
+
+extern "C" TEEFLOW_API int teeflow_selftest_hypot(teeflow_handle h, int mode, int64_t n, uint64_t seed,
+                                                  int64_t* mismatches, int64_t* rejected) {
+    if (!h || !mismatches || !rejected || n < 0 || mode < 0 || mode > 2) return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    CU_TRY(h, cudaSetDevice(h->device));
+    unsigned long long* d = nullptr;
+    CU_TRY(h, cudaMalloc(&d, 2 * sizeof(*d)));
+    CU_TRY(h, cudaMemset(d, 0, 2 * sizeof(*d)));
+    selftest_hypot_kernel<<<h->num_sms * 8, 256>>>((unsigned long long)n, seed, mode, -0.0f, d);
+    unsigned long long out[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(out, d, sizeof(out), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, TEEFLOW_ERR_CUDA, "selftest failed: %s", cudaGetErrorString(e));
+    *mismatches = (int64_t)out[0];
+    *rejected = (int64_t)out[1];
+    return TEEFLOW_OK;
+}
+
 template <typename T>
 static cudaError_t regrow(T*& ptr, size_t count) {
     if (ptr) cudaFree(ptr);
@@ -308,7 +381,7 @@ static cudaError_t regrow(T*& ptr, size_t count) {
     return cudaMalloc((void**)&ptr, count * sizeof(T));
 }
 
-static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_stride, int S, size_t slot_px,
+static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_stride, int S, size_t slot_elems,
                             size_t max_tiles, size_t n_pairs) {
     // a capacity is zeroed before its buffers are reallocated, so a failed cudaMalloc cannot leave a stale size
     if (n_frames * pyr_stride > h->cap_frames * h->cap_pyr_stride) {
@@ -317,10 +390,13 @@ static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_strid
         CU_TRY(h, regrow(h->pyrG, n_frames * pyr_stride));
         h->cap_frames = n_frames; h->cap_pyr_stride = pyr_stride;
     }
-    if ((size_t)S * slot_px > (size_t)h->cap_slots * h->cap_slot_px) {
-        h->cap_slots = 0; h->cap_slot_px = 0;
-        CU_TRY(h, regrow(h->planes, (size_t)S * slot_px * kPlanes));
-        h->cap_slots = S; h->cap_slot_px = slot_px;
+    if ((size_t)S * slot_elems > h->cap_plane_elems) {
+        h->cap_plane_elems = 0; h->planes = nullptr;
+        if (h->planes_raw) cudaFree(h->planes_raw);
+        h->planes_raw = nullptr;
+        CU_TRY(h, cudaMalloc(&h->planes_raw, (size_t)S * slot_elems * sizeof(float2) + kPlaneAlign + 4096));   // + slack past the last row
+        h->planes = (float2*)(((uintptr_t)h->planes_raw + kPlaneAlign - 1) / kPlaneAlign * kPlaneAlign);
+        h->cap_plane_elems = (size_t)S * slot_elems;
     }
     if ((size_t)S * max_tiles > h->cap_tiles) {
         h->cap_tiles = 0;
@@ -350,6 +426,11 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL frames or pair list");
     if (dtype != TEEFLOW_U8 && dtype != TEEFLOW_F32) return fail(h, TEEFLOW_ERR_BAD_ARG, "dtype must be TEEFLOW_U8 or TEEFLOW_F32");
     if (H < 1 || W < 1 || n_frames < 1 || (int64_t)H * W > (1 << 28)) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "bad frame shape %dx%d", H, W);
+    int pitch_i = 0;
+    while (pitch_i < 3 && W + kXMargin > kPitches[pitch_i]) ++pitch_i;
+    if (pitch_i == 3 || (int64_t)(H + 2) * kPlanes * kPitches[pitch_i] >= (1ll << 31))
+        return fail(h, TEEFLOW_ERR_BAD_SHAPE, "frame shape %dx%d exceeds the engine's plane layout (W <= %d)", H, W, kPitches[2] - kXMargin);
+    const int pitch = kPitches[pitch_i];
     if (frame_stride < (int64_t)H * W) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "frame_stride smaller than H*W");
     if (n_pairs < 0) return fail(h, TEEFLOW_ERR_BAD_ARG, "negative pair count");
     if (!flow_f32_dev && !flow_f16_dev) return fail(h, TEEFLOW_ERR_BAD_ARG, "no output buffer");
@@ -389,17 +470,19 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     P.taut = (float)(h->p.tau / h->p.theta);
     P.up_mul = (float)(1.0 / h->p.scale_step);
     P.out_scale = out_scale;
+    P.negzero = -0.0f;
     P.frame_pyr_stride = off;
-    P.slot_px = ((long long)H * W + 63) / 64 * 64;
+    P.pitch = pitch;
+    P.slot_stride = (long long)(H + 2) * kPlanes * pitch;   // two pad rows: the inner iteration's look-ahead loads
     P.max_tiles = std::max(P.lv[0].in_items, 2 * P.lv[0].pw_items);
     if (h->wase_w && (h->wase_H != H || h->wase_W != W))
         return fail(h, TEEFLOW_ERR_BAD_SHAPE, "WASE weight map is %dx%d but the frames are %dx%d", h->wase_H, h->wase_W, H, W);
 
-    int rc = ensure_workspace(h, (size_t)n_frames, (size_t)off, S, (size_t)P.slot_px, (size_t)P.max_tiles, (size_t)n_pairs);
+    int rc = ensure_workspace(h, (size_t)n_frames, (size_t)off, S, (size_t)P.slot_stride, (size_t)P.max_tiles, (size_t)n_pairs);
     if (rc) return rc;
     P.pyrI = h->pyrI; P.pyrG = h->pyrG;
     for (int i = 0; i < 2; ++i) P.slots[i] = h->slots + (size_t)i * kMaxSlots;
-    P.planes = h->planes; P.slot_stride = (long long)kPlanes * P.slot_px;
+    P.planes = h->planes;
     P.arrive = h->arrive; P.partial = h->partial;
     P.next_pair = h->ctl; P.pairs_done = h->ctl + 1; P.item_counter = h->ctl + 2;
     P.pair_a = h->pair_lists; P.pair_b = h->pair_lists + h->cap_pairs;
@@ -452,6 +535,8 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         CU_TRY(h, cudaMemsetAsync(h->arrive, 0, sizeof(unsigned) * kMaxSlots, stream));
         int ctl0[kCtlInts] = {0};
         ctl0[0] = S;
+        // strip counters of launch parity 0: the first strip of a warp is its own index (tvl1_step_kernel)
+        for (int g = 0; g < kMaxGroups; ++g) ctl0[2 + 2 * g] = h->num_sms * h->ctas_per_sm[pitch_i] * kWarpsPerCta;
         CU_TRY(h, cudaMemcpyAsync(h->ctl, ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, stream));
         CU_TRY(h, cudaStreamSynchronize(stream));  // `init` / ctl0 / pair lists are host temporaries
         CU_TRY(h, cudaEventRecord(h->ev_tp, stream));
@@ -461,7 +546,8 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     // drains (its last strips, the launch gap, the next launch's prologue) the other group's strips keep the SMs
     // busy.  The host keeps two chunks of launches in flight per stream and polls the done counter of the chunk
     // before; finished slots make their warps exit at once, so an over-issued launch costs microseconds.
-    const int grid = h->num_sms * h->ctas_per_sm;
+    const int grid = h->num_sms * h->ctas_per_sm[pitch_i];
+    const step_kernel_t step_kernel = step_kernel_for(pitch);
     const int chunk = 16;
     const int G = (S >= 2 * kMinGroupSlots && h->groups > 1) ? std::min(h->groups, kMaxGroups) : 1;
     EngineParams Pg[kMaxGroups];
@@ -486,7 +572,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         if (step > max_steps) return fail(h, TEEFLOW_ERR_STATE, "scheduler exceeded %lld steps", max_steps);
         for (int k = 0; k < chunk; ++k, ++step)
             for (int g = 0; g < G; ++g)
-                tvl1_step_kernel<<<grid, kThreads, 0, gs[g]>>>(Pg[g], (int)(step & 1));
+                step_kernel<<<grid, kThreads, 0, gs[g]>>>(Pg[g], (int)(step & 1));
         CU_TRY(h, cudaGetLastError());
         const int which = n_chunks & 1;
         // join the group streams into the caller's stream at the chunk boundary, then sample the done counter

@@ -18,11 +18,21 @@ namespace teeflow {
 constexpr int kThreads = 256;  // threads per CTA
 constexpr int kWarpsPerCta = kThreads / 32;
 constexpr int kIW = 31;        // inner strip: output columns per warp (lane 31 = right halo column)
-constexpr int kIR = 16;        // inner strip: rows per warp (16 beats 32 / 24 / 12 / 8 once strips are handed out dynamically)
+#ifndef TEEFLOW_STRIP_ROWS
+#define TEEFLOW_STRIP_ROWS 16
+#endif
+constexpr int kIR = TEEFLOW_STRIP_ROWS;   // inner strip: rows per warp (16 beats 32 / 24 / 12 / 8 with dynamic strip hand-out)
 constexpr int kPR = 8;         // pointwise strip: rows per warp (32 columns)
 #ifndef TEEFLOW_DYNAMIC_ITEMS
 #define TEEFLOW_DYNAMIC_ITEMS 1
 #endif
+#ifndef TEEFLOW_INTERLEAVE
+#define TEEFLOW_INTERLEAVE 0   // measured: slot-interleaved hand-out 1043-1053 pairs/s vs 1127 slot by slot (locality wins)
+#endif
+#ifndef TEEFLOW_CHUNK
+#define TEEFLOW_CHUNK 8
+#endif
+constexpr int kChunk = TEEFLOW_CHUNK;   // consecutive strips handed out together (they share halo cache lines)
 
 // ------------------------------------------------------------------------------------------------ pyramid
 // level 0: convertTo(CV_32F, 1) for u8, x255 for f32 (tvl1flow.cpp: I0mult / I1mult)
@@ -132,86 +142,86 @@ __device__ __forceinline__ int items_of(const EngineParams& P, int phase, int pa
 }
 
 // ------------------------------------------------------------------------------------------------ strip ops
-// All slot planes are addressed as  slot base (one 64-bit pointer) + 32-bit float2 element index.
+// Slot planes live in the row-interleaved constant-pitch layout of struct Lay (tvl1_device.cuh).
 __device__ __forceinline__ float2* slot_base(const EngineParams& P, int slot) {
     return P.planes + (size_t)slot * (size_t)P.slot_stride;
 }
-__device__ __forceinline__ unsigned plane_at(const EngineParams& P, unsigned plane) { return plane * (unsigned)P.slot_px; }
 
 // PH_LEVEL_INIT: u = 0 (coarsest) or u = resize(u_coarse, INTER_LINEAR) * (1/scaleStep); p = 0
+template <int PITCH>
 __device__ __forceinline__ void op_level_init(const EngineParams& P, int level, int ucur, int slot, int strip, int lane) {
+    using L = Lay<PITCH>;
     const LevelGeom& g = P.lv[level];
     float2* SB = slot_base(P, slot);
     const bool coarsest = (level == P.L - 1);
-    const unsigned oUd = plane_at(P, PL_U + (coarsest ? 0u : (unsigned)(ucur ^ 1)));
-    const unsigned oUs = plane_at(P, PL_U + (unsigned)ucur);
-    const unsigned oPX = plane_at(P, PL_PX), oPY = plane_at(P, PL_PY);
+    const unsigned pUd = PL_U + (coarsest ? 0u : (unsigned)(ucur ^ 1));
+    const unsigned pUs = PL_U + (unsigned)ucur;
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
     int x0 = 0, x1 = 0; float a0 = 0.f, a1 = 0.f;
-    int cH = 0, cW = 0;
+    int cH = 0;
     if (!coarsest) {
-        cH = P.lv[level + 1].H; cW = P.lv[level + 1].W;
-        lin_coeff_x(x, g.up_sx, cW, x0, x1, a0, a1);
+        cH = P.lv[level + 1].H;
+        lin_coeff_x(x, g.up_sx, P.lv[level + 1].W, x0, x1, a0, a1);
     }
     for (int y = y0; y < y1; ++y) {
-        const unsigned q = (unsigned)(y * g.W + x);
         float2 u = make_float2(0.f, 0.f);
         if (!coarsest) {
             int ya, yb; float b0, b1;
             lin_coeff_y(y, g.up_sy, cH, ya, yb, b0, b1);
-            const float2 s00 = SB[oUs + (unsigned)(ya * cW + x0)], s01 = SB[oUs + (unsigned)(ya * cW + x1)];
-            const float2 s10 = SB[oUs + (unsigned)(yb * cW + x0)], s11 = SB[oUs + (unsigned)(yb * cW + x1)];
+            const float2 s00 = SB[L::at(pUs, ya, x0)], s01 = SB[L::at(pUs, ya, x1)];
+            const float2 s10 = SB[L::at(pUs, yb, x0)], s11 = SB[L::at(pUs, yb, x1)];
             const float r0x = s00.x * a0 + s01.x * a1, r1x = s10.x * a0 + s11.x * a1;
             const float r0y = s00.y * a0 + s01.y * a1, r1y = s10.y * a0 + s11.y * a1;
             u.x = (r0x * b0 + r1x * b1) * P.up_mul;
             u.y = (r0y * b0 + r1y * b1) * P.up_mul;
         }
-        SB[oUd + q] = u;
-        SB[oPX + q] = make_float2(0.f, 0.f);
-        SB[oPY + q] = make_float2(0.f, 0.f);
+        SB[L::at(pUd, y, x)] = u;
+        SB[L::at(PL_PX, y, x)] = make_float2(0.f, 0.f);
+        SB[L::at(PL_PY, y, x)] = make_float2(0.f, 0.f);
     }
 }
 
 // PH_WARP: buildFlowMap + remap(I1, I1x, I1y; INTER_CUBIC) + calcGradRho
+template <int PITCH>
 __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int ucur, int pair, int slot, int strip,
                                         int lane, const float4* s_cubic) {
+    using L = Lay<PITCH>;
     const LevelGeom& g = P.lv[level];
     float2* SB = slot_base(P, slot);
-    const float2* U = SB + plane_at(P, PL_U + (unsigned)ucur);
-    float4* COEF = reinterpret_cast<float4*>(SB + plane_at(P, PL_COEF));
     const int fa = P.pair_a[pair], fb = P.pair_b[pair];
     const float* I0 = P.pyrI + (size_t)fa * P.frame_pyr_stride + g.pyr_off;
     const float4* G1 = P.pyrG + (size_t)fb * P.frame_pyr_stride + g.pyr_off;
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
+    float2* row = SB + L::at(0, y0, x);          // plane 0 of row y0; planes / rows at constant offsets
+    const unsigned oU = (PL_U + (unsigned)ucur) * (unsigned)PITCH;
     // the flow / I0 of the next row are fetched while the current row's gather runs (one row ahead)
-    float2 u_n = __ldg(U + (unsigned)(y0 * g.W + x));
+    float2 u_n = __ldg(row + oU);
     float i0_n = __ldg(I0 + (unsigned)(y0 * g.W + x));
     for (int y = y0; y < y1; ++y) {
         const unsigned q = (unsigned)(y * g.W + x);
         const float2 u = u_n;
         const float i0 = i0_n;
-        if (y + 1 < y1) { u_n = __ldg(U + q + (unsigned)g.W); i0_n = __ldg(I0 + q + (unsigned)g.W); }
+        if (y + 1 < y1) { u_n = __ldg(row + oU + L::ROW); i0_n = __ldg(I0 + q + (unsigned)g.W); }
         const float mx = (float)x + u.x, my = (float)y + u.y;
         const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic);
         const float Ix2 = w.y * w.y, Iy2 = w.z * w.z;
-        float4 c;
-        c.x = w.y; c.y = w.z;
-        c.z = Ix2 + Iy2;
-        c.w = (w.x - w.y * u.x - w.z * u.y - i0);
-        COEF[q] = c;
+        row[PL_CA * PITCH] = make_float2(w.y, w.z);
+        row[PL_CB * PITCH] = make_float2(Ix2 + Iy2, (w.x - w.y * u.x - w.z * u.y - i0));
+        row += L::ROW;
     }
 }
 
 // PH_MEDIAN: medianBlur(u1, ksize), medianBlur(u2, ksize) with BORDER_REPLICATE
+template <int PITCH>
 __device__ __forceinline__ void op_median(const EngineParams& P, int level, int ucur, int slot, int strip, int lane) {
+    using L = Lay<PITCH>;
     const LevelGeom& g = P.lv[level];
     float2* SB = slot_base(P, slot);
-    const float2* __restrict__ Us = SB + plane_at(P, PL_U + (unsigned)ucur);
-    float2* __restrict__ Ud = SB + plane_at(P, PL_U + (unsigned)(ucur ^ 1));
+    const unsigned pUs = PL_U + (unsigned)ucur, pUd = PL_U + (unsigned)(ucur ^ 1);
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
@@ -225,7 +235,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
 #pragma unroll
                 for (int dx = -2; dx <= 2; ++dx) {
                     const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = __ldg(Us + (unsigned)(yy * g.W + xx));
+                    const float2 t = __ldg(SB + L::at(pUs, yy, xx));
                     v[(dy + 2) * 5 + dx + 2] = t.x;
                     w[(dy + 2) * 5 + dx + 2] = t.y;
                 }
@@ -240,7 +250,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = __ldg(Us + (unsigned)(yy * g.W + xx));
+                    const float2 t = __ldg(SB + L::at(pUs, yy, xx));
                     v[(dy + 1) * 3 + dx + 1] = t.x;
                     w[(dy + 1) * 3 + dx + 1] = t.y;
                 }
@@ -248,39 +258,60 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
             out.x = median9(v);
             out.y = median9(w);
         }
-        Ud[(unsigned)(y * g.W + x)] = out;
+        SB[L::at(pUd, y, x)] = out;
     }
 }
 
 // ---- inner iteration pieces -------------------------------------------------------------------------------
-struct InnerRow { float2 u; float4 c; float2 px, py, pxl; };
+// The two flow channels are packed in float2 values and go through f32x2 instructions; every half rounds like
+// the scalar operation of the C++ source.  Each piece has a branch-free FAST form that also reports whether its
+// result can be trusted (operands inside the domain on which the fast sequence is proven exact) and an EXACT form
+// (IEEE division, double-precision hypot); a row takes one merged branch to the exact forms when any lane needs it.
+struct InnerRow { float2 u, ca, cb, px, py, pxl; };   // ca = (I1wx, I1wy), cb = (grad, rho_c)
+struct InnerConst { float l_t, theta, taut, negzero; };
 
-// estimateV + divergence + estimateU for one pixel (tvl1flow.cpp order of operations), branch-free: the
-// thresholding division runs on every lane through the shared fast path and is selected where it applies.
-__device__ __forceinline__ float2 estimate_u_px(const InnerRow& r, float2 pxl, float2 pyu, bool x_is_0, bool y_is_0,
-                                                float l_t, float theta) {
-    const float4 c = r.c;
-    const float rho = c.w + (c.x * r.u.x + c.y * r.u.y);
-    const float lg = l_t * c.z;
+// estimateV: d = v - u.  c3_bad: the thresholding division ran outside the fast path's domain (needs_exact).
+struct VStep { float2 d; float nrho, grad; bool bad; };
+__device__ __forceinline__ VStep estimate_v_fast(const InnerRow& r, const InnerConst& K) {
+    VStep o;
+    const float2 cu = mul2(r.ca, r.u);
+    const float rho = r.cb.y + (cu.x + cu.y);
+    const float grad = r.cb.x;
+    const float lg = K.l_t * grad;
     const bool c1 = rho < -lg;
     const bool c2 = !c1 && rho > lg;
-    const bool c3 = !c1 && !c2 && c.z > FLT_EPSILON;
-    const float nrho = -rho;
-    float fi = div_with_rcp(nrho, c.z, refined_rcp(c.z));
-    if (c3 && !(div_den_ok(c.z) && div_fast_ok(nrho))) fi = __fdiv_rn(nrho, c.z);   // rare: IEEE slow path
-    const float a1 = l_t * c.x, a2 = l_t * c.y;
-    const float d1 = c1 ? a1 : (c2 ? -a1 : (c3 ? fi * c.x : 0.f));
-    const float d2 = c1 ? a2 : (c2 ? -a2 : (c3 ? fi * c.y : 0.f));
-    const float v1 = r.u.x + d1, v2 = r.u.y + d2;
-    float div1, div2;
-    if (x_is_0 && !y_is_0) {          // first column: v1 + v2 - v2(y-1)
-        div1 = r.px.x + r.py.x - pyu.x;
-        div2 = r.px.y + r.py.y - pyu.y;
-    } else {                          // interior; first row / corner follow with the missing terms == 0
-        div1 = (r.px.x - pxl.x) + (r.py.x - pyu.x);
-        div2 = (r.px.y - pxl.y) + (r.py.y - pyu.y);
+    const bool c3 = !c1 && !c2 && grad > FLT_EPSILON;
+    o.nrho = -rho; o.grad = grad;
+    const float fi = div_with_rcp(o.nrho, grad, refined_rcp(grad));
+    // in case 3, 2^-23 < grad and |rho| <= l_t * grad: of div_den_ok / div_fast_ok only these bounds can fail
+    o.bad = c3 && (grad > 1.0995116e12f || (fabsf(rho) < 8.6736174e-19f && rho != 0.0f));
+    // d = (l_t | -l_t | fi) * (I1wx, I1wy); (-l_t) * c == -(l_t * c) exactly
+    const float k = c1 ? K.l_t : (c2 ? -K.l_t : fi);
+    o.d = mul2(r.ca, splat2(k));
+    if (!(c1 || c2 || c3)) o.d = make_float2(0.f, 0.f);
+    return o;
+}
+__device__ __forceinline__ float2 estimate_v_exact(const InnerRow& r, const VStep& v) {   // only reached in case 3
+    return mul2(r.ca, splat2(__fdiv_rn(v.nrho, v.grad)));
+}
+
+// theta * divergence(p) for one pixel
+__device__ __forceinline__ float2 theta_div_px(const InnerRow& r, float2 pxl, float2 pyu, bool strip_at_x0,
+                                               bool first_col_not_first_row, const InnerConst& K) {
+    float2 dv = add2(sub2(r.px, pxl), sub2(r.py, pyu));      // interior; first row / corner: missing terms == 0
+    if (strip_at_x0) {                                       // warp-uniform
+        const float2 alt = sub2(add2(r.px, r.py), pyu);      // first column: v1 + v2 - v2(y-1)
+        if (first_col_not_first_row) dv = alt;
     }
-    return make_float2(v1 + theta * div1, v2 + theta * div2);
+    return mul2_nofuse(dv, splat2(K.theta), K.negzero);
+}
+
+// estimateV + divergence + estimateU for one pixel (tvl1flow.cpp order of operations), self-contained form
+__device__ __forceinline__ float2 estimate_u_px(const InnerRow& r, float2 pxl, float2 pyu, bool strip_at_x0,
+                                                bool first_col_not_first_row, const InnerConst& K) {
+    VStep v = estimate_v_fast(r, K);
+    if (v.bad) v.d = estimate_v_exact(r, v);
+    return add2(add2(r.u, v.d), theta_div_px(r, pxl, pyu, strip_at_x0, first_col_not_first_row, K));
 }
 
 __device__ __forceinline__ float hypot_f(float a, float b) {
@@ -289,101 +320,201 @@ __device__ __forceinline__ float hypot_f(float a, float b) {
     return (float)sqrt((double)a * (double)a + (double)b * (double)b);
 }
 
+// (hypot_f(a.x, b.x), hypot_f(a.y, b.y)) without double precision.
+// s = a^2 + b^2 is held exactly as an unevaluated float sum (S + low: products split by fma, sum by two-sum);
+// h = S * rsqrt(S) is corrected by one Newton step on the exact residual: h + c is within 2^-42 (relative) of the
+// double-precision value the reference rounds to float.  Rounding h + c + delta and h + c - delta, with
+// delta = 2^-37 h + 2^-15 |c| far above that error, gives the same float unless a rounding boundary is that close
+// (probability ~2^-12 per value) -- by monotonicity of rounding that float is then the reference's result.
+// ok = false also when s overflows (NaN: the comparison fails) or the operands are non-zero but below 2^-45.
+__device__ __forceinline__ float2 hypot2_fast(float2 a, float2 b, float negzero, bool& ok) {
+    const float2 A = mul2_nofuse(a, a, negzero), B = mul2_nofuse(b, b, negzero);   // they feed S = A + B
+    const float2 Ae = fma2(a, a, neg2(A)), Be = fma2(b, b, neg2(B));
+    const float2 S = add2(A, B);
+    const float2 Bv = sub2(S, A), Av = sub2(S, Bv);
+    const float2 Se = add2(sub2(A, Av), sub2(B, Bv));
+    const float2 low = add2(Se, add2(Ae, Be));
+    float2 y;   // s == 0 -> y = 2^50, h = c = 0, result 0
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(fmaxf(S.x, 7.888609e-31f)));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(fmaxf(S.y, 7.888609e-31f)));
+    const float2 h = mul2(S, y);
+    const float2 rr = add2(fma2(neg2(h), h, S), low);
+    const float2 c = mul2(rr, mul2(y, splat2(0.5f)));
+    const float2 cabs = make_float2(fabsf(c.x), fabsf(c.y));
+    const float2 delta = fma2(cabs, splat2(3.0517578e-5f), mul2(h, splat2(7.2759576e-12f)));   // 2^-15, 2^-37
+    const float2 g1 = add2(h, add2(c, delta)), g2 = add2(h, sub2(c, delta));
+    // a == b == 0 is exact; otherwise max(|a|, |b|) < 2^-45 is refused (the squares and their split parts underflow)
+    const unsigned mx = __float_as_uint(fmaxf(fabsf(a.x), fabsf(b.x))), my = __float_as_uint(fmaxf(fabsf(a.y), fabsf(b.y)));
+    const bool in_range = (mx - 1u) >= (0x29000000u - 1u) && (my - 1u) >= (0x29000000u - 1u);
+    ok = in_range && (g1.x == g2.x) && (g1.y == g2.y);
+    return g1;
+}
+
+// forwardGradient(u_new) + estimateDualVariables for one pixel: ux = (u1x, u2x), uy = (u1y, u2y),
+// px = (p11, p21), py = (p12, p22); pxn / pyn receive the updated dual variables.  Returns false when the fast
+// sequences were outside their domain (then pxn / pyn are not valid and dual_update_exact must be used).
+__device__ __forceinline__ bool dual_update_fast(float2 ux, float2 uy, float2 px, float2 py, const InnerConst& K,
+                                                 float2& pxn, float2& pyn) {
+    bool hyp_ok;
+    const float2 gg = hypot2_fast(ux, uy, K.negzero, hyp_ok);
+    const float2 taut2 = splat2(K.taut);
+    const float2 ng = add2(splat2(1.0f), mul2_nofuse(taut2, gg, K.negzero));
+    const float2 ax = add2(px, mul2_nofuse(taut2, ux, K.negzero));    // (a11, a21)
+    const float2 ay = add2(py, mul2_nofuse(taut2, uy, K.negzero));    // (a12, a22)
+    // one guard for the four numerators: every |a| is 0 or >= 2^-100, the largest <= 2^100; ng in [1, 2^20]
+    const float amax = fmaxf(fmaxf(fabsf(ax.x), fabsf(ay.x)), fmaxf(fabsf(ax.y), fabsf(ay.y)));
+    const bool tiny = dual_num_tiny(ax.x) || dual_num_tiny(ay.x) || dual_num_tiny(ax.y) || dual_num_tiny(ay.y);
+    // refined_rcp + div_with_rcp of tvl1_device.cuh, two channels per instruction
+    float2 r0;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.x) : "f"(ng.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0.y) : "f"(ng.y));
+    const float2 mng = neg2(ng);
+    const float2 r = fma2(r0, fma2(mng, r0, splat2(1.0f)), r0);
+    const float2 zero = splat2(0.0f);
+    const float2 qx0 = fma2(ax, r, zero), qy0 = fma2(ay, r, zero);
+    const float2 qx = fma2(r, fma2(mng, qx0, ax), qx0), qy = fma2(r, fma2(mng, qy0, ay), qy0);
+    pxn = make_float2(or_sign(qx.x, ax.x), or_sign(qx.y, ax.y));
+    pyn = make_float2(or_sign(qy.x, ay.x), or_sign(qy.y, ay.y));
+    return hyp_ok && dual_ok(tiny, amax, fmaxf(ng.x, ng.y));
+}
+__device__ __forceinline__ void dual_update_exact(float2 ux, float2 uy, float2 px, float2 py, const InnerConst& K,
+                                                  float2& pxn, float2& pyn) {
+    const float g1 = hypot_f(ux.x, uy.x), g2 = hypot_f(ux.y, uy.y);
+    const float ng1 = 1.0f + K.taut * g1, ng2 = 1.0f + K.taut * g2;
+    pxn.x = __fdiv_rn(px.x + K.taut * ux.x, ng1); pyn.x = __fdiv_rn(py.x + K.taut * uy.x, ng1);
+    pxn.y = __fdiv_rn(px.y + K.taut * ux.y, ng2); pyn.y = __fdiv_rn(py.y + K.taut * uy.y, ng2);
+}
+
+__device__ __forceinline__ float and_mask(float v, unsigned m) { return __uint_as_float(__float_as_uint(v) & m); }
+__device__ __forceinline__ float and_or(float v, unsigned m, float o) {   // (v & m) | o : one LOP3
+    return __uint_as_float((__float_as_uint(v) & m) | __float_as_uint(o));
+}
+
 // PH_INNER: one primal-dual iteration, warp-autonomous register-rolling strip.
-// Addressing: one slot base pointer + seven 32-bit element indices that advance by W per row.
+// A warp owns kIW output columns (+1 halo column in lane 31) and walks down kIR rows; vertical neighbours stay in
+// registers, horizontal ones come by warp shuffle, the loads of row y+2 are in flight while row y+1 is computed.
+// Addressing: three row pointers (U, P, coefficient planes) advanced by one image row per iteration; every plane,
+// the row look-ahead and the ping-pong partners are immediate offsets / one XOR from them.  Slots carry two pad
+// rows below the image, so the look-ahead loads need no bounds test.  (A shared-memory ring filled by 16-byte
+// cp.async copies, 2-4 rows deep, was measured: not faster -- the pure inner launch already runs at ~80 % of the
+// HBM peak with this one-row register look-ahead -- and its 46 KB per CTA cost the other phases their L1.)
+template <int PITCH>
 __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int ucur, int pcur, int slot, int strip,
                                            int lane) {
+    using L = Lay<PITCH>;
+    constexpr int PB = (int)L::PB, ROWB = (int)L::ROWB;
     const LevelGeom& g = P.lv[level];
     const int W = g.W, H = g.H;
-    float2* __restrict__ SB = slot_base(P, slot);
-    const float4* __restrict__ SB4 = reinterpret_cast<const float4*>(SB);
-    const float l_t = P.l_t, theta = P.theta, taut = P.taut;
+    const InnerConst K = {P.l_t, P.theta, P.taut, P.negzero};
 
     const int x0 = (strip % g.in_sx) * kIW;
     const int y0 = (strip / g.in_sx) * kIR, y1 = min(y0 + kIR, H);
     const int x = x0 + lane;
     const bool valid = x < W;                    // lane computes u_new
     const bool owner = valid && lane < kIW;      // lane owns the outputs of its column
-    const bool has_right = x + 1 < W;
-    const bool x_is_0 = (x == 0);
+    const unsigned right_mask = (x + 1 < W) ? 0xffffffffu : 0u;   // forward x-difference exists
+    const unsigned not_lane0 = lane == 0 ? 0u : 0xffffffffu;
+    const bool strip_at_x0 = (x0 == 0);          // warp-uniform
+    const bool first_col = (x == 0);
     const bool lane0_left = (lane == 0 && x0 > 0);
     const int xc = valid ? x : W - 1;            // clamp: idle lanes read a legal address
-    const unsigned q0 = (unsigned)(y0 * W + xc); // pixel offset of the strip's first row
-    // element indices (float2 units; COEF in float4 units) of row y, advanced by W per row
-    unsigned iU = plane_at(P, PL_U + (unsigned)ucur) + q0, iUn = plane_at(P, PL_U + (unsigned)(ucur ^ 1)) + q0;
-    unsigned iPX = plane_at(P, PL_PX + (unsigned)pcur) + q0, iPXn = plane_at(P, PL_PX + (unsigned)(pcur ^ 1)) + q0;
-    unsigned iPY = plane_at(P, PL_PY + (unsigned)pcur) + q0, iPYn = plane_at(P, PL_PY + (unsigned)(pcur ^ 1)) + q0;
-    unsigned iC = (plane_at(P, PL_COEF) >> 1) + q0;
-    const unsigned uW = (unsigned)W;
+    const char* base = reinterpret_cast<const char*>(slot_base(P, slot)) + ((size_t)y0 * (size_t)ROWB + (size_t)(xc + kXMargin) * 8u);
+    const char* pu = base + ucur * PB;                  // U[ucur] of row y        (partner: ^ PB)
+    const char* pp = base + ((int)PL_PX + pcur) * PB;   // PX[pcur]; PY[pcur] at + 2 PB (partners: ^ PB)
+    const char* pc = base + (int)PL_CA * PB;            // CA; CB at + PB
 
-    auto load_row = [&](unsigned rows_ahead) {
-        const unsigned d = rows_ahead * uW;
+    auto ld = [](const char* p, int off) { return __ldg(reinterpret_cast<const float2*>(p + off)); };
+    // ping-pong partner plane: one XOR when PB is a power of two (address bits of row / plane / column are disjoint),
+    // else an add of +-PB
+    const int du = ucur ? -PB : PB, dp = pcur ? -PB : PB;
+    auto partner_u = [&](const char* p) {
+        if constexpr ((PB & (PB - 1)) == 0) return reinterpret_cast<char*>(reinterpret_cast<uintptr_t>(p) ^ (uintptr_t)PB);
+        else return const_cast<char*>(p) + du;
+    };
+    auto partner_p = [&](const char* p) {
+        if constexpr ((PB & (PB - 1)) == 0) return reinterpret_cast<char*>(reinterpret_cast<uintptr_t>(p) ^ (uintptr_t)PB);
+        else return const_cast<char*>(p) + dp;
+    };
+    auto st = [](char* p, int off, float2 v) { *reinterpret_cast<float2*>(p + off) = v; };
+    auto load_row = [&](int rows_ahead) {
+        const int d = rows_ahead * ROWB;
         InnerRow r;
-        r.u = __ldg(SB + iU + d);
-        r.c = __ldg(SB4 + iC + d);
-        r.px = __ldg(SB + iPX + d);
-        r.py = __ldg(SB + iPY + d);
+        r.u = ld(pu, d);
+        r.ca = ld(pc, d);
+        r.cb = ld(pc, d + PB);
+        r.px = ld(pp, d);
+        r.py = ld(pp, d + 2 * PB);
         r.pxl = make_float2(0.f, 0.f);
-        if (lane0_left) r.pxl = __ldg(SB + iPX + d - 1);   // only lane 0 of a strip that does not start at x = 0
+        if (lane0_left) r.pxl = ld(pp, d - 8);   // only lane 0 of a strip that does not start at x = 0
         return r;
+    };
+    // left neighbour's px: by shuffle, lane 0 takes the value it loaded itself (zero at the image border)
+    auto left_px = [&](const InnerRow& r) {
+        return make_float2(and_or(__shfl_up_sync(0xffffffffu, r.px.x, 1), not_lane0, r.pxl.x),
+                           and_or(__shfl_up_sync(0xffffffffu, r.px.y, 1), not_lane0, r.pxl.y));
+    };
+    // forward x-difference of u_new (zero in the last image column)
+    auto diff_x = [&](float2 un) {
+        const float2 d = sub2(make_float2(__shfl_down_sync(0xffffffffu, un.x, 1), __shfl_down_sync(0xffffffffu, un.y, 1)), un);
+        return make_float2(and_mask(d.x, right_mask), and_mask(d.y, right_mask));
     };
 
     double err = 0.0;
     float2 pyu = make_float2(0.f, 0.f);
-    if (y0 > 0) pyu = __ldg(SB + iPY - uW);
-    InnerRow cur = load_row(0);
-    InnerRow nxt = cur;
-    if (y0 + 1 < H) nxt = load_row(1);
+    if (y0 > 0) pyu = ld(pp, 2 * PB - ROWB);
+    const InnerRow cur = load_row(0);
+    InnerRow nxt = load_row(1);                  // row y0 + 1 <= H: inside the image or the first pad row
 
-    float2 pxl = make_float2(__shfl_up_sync(0xffffffffu, cur.px.x, 1), __shfl_up_sync(0xffffffffu, cur.px.y, 1));
-    if (lane == 0) pxl = cur.pxl;
-    float2 un = estimate_u_px(cur, pxl, pyu, x_is_0, y0 == 0, l_t, theta);
+    float2 un = estimate_u_px(cur, left_px(cur), pyu, strip_at_x0, first_col && y0 > 0, K);
     if (owner) {
-        SB[iUn] = un;
-        const float t = (un.x - cur.u.x) * (un.x - cur.u.x) + (un.y - cur.u.y) * (un.y - cur.u.y);
-        err += (double)t;
+        st(partner_u(pu), 0, un);
+        const float2 du = sub2(un, cur.u);
+        const float2 sq = mul2(du, du);
+        err += (double)(sq.x + sq.y);
     }
     float2 px_c = cur.px, py_c = cur.py;
 
+    // rows y0 .. y1-2: row y+1 belongs to this strip (u_new stored, error counted); row y+2 <= H is prefetched
 #pragma unroll 2
-    for (int y = y0; y < y1; ++y) {
-        const bool has_next = (y + 1 < H);       // warp-uniform
-        float2 un_n = make_float2(0.f, 0.f);
-        InnerRow row = nxt;                      // row y+1 (already in flight)
-        if (y + 2 < H && y + 1 < y1) nxt = load_row(2);
-        if (has_next) {
-            float2 pl = make_float2(__shfl_up_sync(0xffffffffu, row.px.x, 1), __shfl_up_sync(0xffffffffu, row.px.y, 1));
-            if (lane == 0) pl = row.pxl;
-            un_n = estimate_u_px(row, pl, py_c, x_is_0, false, l_t, theta);
-            if (owner && y + 1 < y1) {
-                SB[iUn + uW] = un_n;
-                const float t = (un_n.x - row.u.x) * (un_n.x - row.u.x) + (un_n.y - row.u.y) * (un_n.y - row.u.y);
-                err += (double)t;
-            }
-        }
-        // forwardGradient(u_new) + estimateDualVariables for row y
-        const float unr_x = __shfl_down_sync(0xffffffffu, un.x, 1), unr_y = __shfl_down_sync(0xffffffffu, un.y, 1);
-        const float u1x = has_right ? unr_x - un.x : 0.f, u2x = has_right ? unr_y - un.y : 0.f;
-        const float u1y = has_next ? un_n.x - un.x : 0.f, u2y = has_next ? un_n.y - un.y : 0.f;
-        const float g1 = hypot_f(u1x, u1y), g2 = hypot_f(u2x, u2y);
-        const float ng1 = 1.0f + taut * g1, ng2 = 1.0f + taut * g2;
-        const float a11 = px_c.x + taut * u1x, a12 = py_c.x + taut * u1y;
-        const float a21 = px_c.y + taut * u2x, a22 = py_c.y + taut * u2y;
+    for (int y = y0; y < y1 - 1; ++y) {
+        const InnerRow row = nxt;                // row y+1 (already in flight)
+        nxt = load_row(2);
+        // u_new of row y+1, then forwardGradient(u_new) + estimateDualVariables of row y -- fast forms
+        VStep v = estimate_v_fast(row, K);
+        const float2 tdv = theta_div_px(row, left_px(row), py_c, strip_at_x0, first_col, K);
+        float2 un_n = add2(add2(row.u, v.d), tdv);
+        const float2 ux = diff_x(un);
         float2 pxn, pyn;
-        // one guard for the four numerators: every |a| is 0 or >= 2^-100, the largest <= 2^100; ng in [1, 2^20]
-        const float amax = fmaxf(fmaxf(fabsf(a11), fabsf(a12)), fmaxf(fabsf(a21), fabsf(a22)));
-        const bool tiny = dual_num_tiny(a11) || dual_num_tiny(a12) || dual_num_tiny(a21) || dual_num_tiny(a22);
-        if (dual_ok(tiny, amax, fmaxf(ng1, ng2))) {
-            const float r1 = refined_rcp(ng1), r2 = refined_rcp(ng2);
-            pxn.x = div_with_rcp(a11, ng1, r1); pyn.x = div_with_rcp(a12, ng1, r1);
-            pxn.y = div_with_rcp(a21, ng2, r2); pyn.y = div_with_rcp(a22, ng2, r2);
-        } else {
-            pxn.x = __fdiv_rn(a11, ng1); pyn.x = __fdiv_rn(a12, ng1);
-            pxn.y = __fdiv_rn(a21, ng2); pyn.y = __fdiv_rn(a22, ng2);
+        const bool ok = dual_update_fast(ux, sub2(un_n, un), px_c, py_c, K, pxn, pyn);
+        if (v.bad || !ok) {                      // rare: redo this lane's row with the exact forms
+            if (v.bad) un_n = add2(add2(row.u, estimate_v_exact(row, v)), tdv);
+            dual_update_exact(ux, sub2(un_n, un), px_c, py_c, K, pxn, pyn);
         }
-        if (owner) { SB[iPXn] = pxn; SB[iPYn] = pyn; }
+        if (owner) {
+            char* puw = partner_u(pu);
+            char* ppw = partner_p(pp);
+            st(puw, ROWB, un_n);
+            st(ppw, 0, pxn);
+            st(ppw, 2 * PB, pyn);
+            const float2 du = sub2(un_n, row.u);
+            const float2 sq = mul2(du, du);
+            err += (double)(sq.x + sq.y);
+        }
         un = un_n; px_c = row.px; py_c = row.py;
-        iU += uW; iUn += uW; iPX += uW; iPXn += uW; iPY += uW; iPYn += uW; iC += uW;
+        pu += ROWB; pp += ROWB; pc += ROWB;
+    }
+    // last row of the strip (y = y1-1): u_new of row y1 is only needed for the y-difference (the next strip owns it)
+    {
+        float2 uy = make_float2(0.f, 0.f);
+        if (y1 < H) {                            // warp-uniform
+            const float2 un_n = estimate_u_px(nxt, left_px(nxt), py_c, strip_at_x0, first_col, K);
+            uy = sub2(un_n, un);
+        }
+        const float2 ux = diff_x(un);
+        float2 pxn, pyn;
+        if (!dual_update_fast(ux, uy, px_c, py_c, K, pxn, pyn)) dual_update_exact(ux, uy, px_c, py_c, K, pxn, pyn);
+        char* ppw = partner_p(pp);
+        if (owner) { st(ppw, 0, pxn); st(ppw, 2 * PB, pyn); }
     }
     // fixed-order warp reduction of the float64 error partial
 #pragma unroll
@@ -399,10 +530,12 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 // PH_WASE: background = mean(masked_flow[masked_flow != 0]) with masked_flow = flow * bkgd[all N frames]
 // (calculate_optical_flow.py:649-652) == sum(w f [f != 0]) / sum(w [f != 0]) with w = sum_n bkgd[n]  (float64 sums)
+template <int PITCH>
 __device__ __forceinline__ void op_wase(const EngineParams& P, int ucur, int slot, int strip, int lane, double& sum,
                                         double& cnt) {
+    using L = Lay<PITCH>;
     const LevelGeom& g = P.lv[0];
-    const float2* U = slot_base(P, slot) + plane_at(P, PL_U + (unsigned)ucur);
+    const float2* SB = slot_base(P, slot);
     const float2* Wt = reinterpret_cast<const float2*>(P.wase_w);
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
@@ -410,7 +543,7 @@ __device__ __forceinline__ void op_wase(const EngineParams& P, int ucur, int slo
     if (x < g.W) {
         for (int y = y0; y < y1; ++y) {
             const unsigned q = (unsigned)(y * g.W + x);
-            const float2 u = U[q];
+            const float2 u = SB[L::at(PL_U + (unsigned)ucur, y, x)];
             const float2 w = __ldg(Wt + q);
             if (u.x != 0.f) { sum += (double)w.x * (double)u.x; cnt += (double)w.x; }
             if (u.y != 0.f) { sum += (double)w.y * (double)u.y; cnt += (double)w.y; }
@@ -425,10 +558,12 @@ __device__ __forceinline__ void op_wase(const EngineParams& P, int ucur, int slo
 
 // PH_FINAL: (merge(u1,u2) - background) * conversion_factor -> (H,W,2) f32 and/or f16
 // (calculate_optical_flow.py:659, 600, 403)
+template <int PITCH>
 __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pair, float bg, int slot, int strip,
                                          int lane) {
+    using L = Lay<PITCH>;
     const LevelGeom& g = P.lv[0];
-    const float2* U = slot_base(P, slot) + plane_at(P, PL_U + (unsigned)ucur);
+    const float2* SB = slot_base(P, slot);
     const size_t npx = (size_t)g.H * g.W;
     const int o0 = P.out_index[pair], o1 = P.dup_index[pair];
     const int x = (strip % g.pw_sx) * 32 + lane;
@@ -436,7 +571,7 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
     if (x >= g.W) return;
     for (int y = y0; y < y1; ++y) {
         const unsigned q = (unsigned)(y * g.W + x);
-        float2 u = U[q];
+        float2 u = SB[L::at(PL_U + (unsigned)ucur, y, x)];
         u.x = (u.x - bg) * P.out_scale;
         u.y = (u.y - bg) * P.out_scale;
         if (P.flow_f32) {
@@ -455,6 +590,7 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
 #ifndef TEEFLOW_MIN_CTAS
 #define TEEFLOW_MIN_CTAS 4
 #endif
+template <int PITCH>
 __global__ void __launch_bounds__(kThreads, TEEFLOW_MIN_CTAS)
 tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     __shared__ int s_prefix[kMaxSlots + 1];
@@ -475,6 +611,21 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     }
     __syncthreads();
     const int total = s_prefix[P.S];
+#if TEEFLOW_INTERLEAVE
+    // Slot-interleaved hand-out: chunk C of kChunk consecutive strips -> slot C % S, chunk C / S of that slot.  At
+    // every moment the running warps work on ALL slots of the group (a few consecutive chunks of each, so the strips
+    // of one slot are still visited in raster order): the HBM-bound phase (inner) and the ALU-bound ones (median,
+    // warp) of different slots share every SM instead of alternating slot by slot.  Draws beyond a slot's last
+    // strip are skipped.
+    __shared__ int s_maxn;
+    if (tid == 0) {
+        int m = 0;
+        for (int q = 0; q < P.S; ++q) m = max(m, s_prefix[q + 1] - s_prefix[q]);
+        s_maxn = m;
+    }
+    __syncthreads();
+    const int n_draws = P.S * ((s_maxn + kChunk - 1) / kChunk) * kChunk;
+#endif
 
     // slots without work this step: carry their state over to the other parity unchanged
     if (blockIdx.x == 0)
@@ -484,33 +635,50 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
 #if TEEFLOW_DYNAMIC_ITEMS
     // dynamic distribution: every warp pulls the next strip from a per-launch counter, so strips of unequal cost
     // (inner / median / warp phases mix in one launch) balance out; the counter of the other parity is re-armed
-    if (blockIdx.x == 0 && tid == 0) P.item_counter[parity ^ 1] = 0;
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(P.item_counter + parity, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
+    // The first strip of every warp is its global warp index (no burst of same-address atomics at launch); the
+    // counter therefore starts at the number of warps of the grid.
+    if (blockIdx.x == 0 && tid == 0) P.item_counter[parity ^ 1] = (int)gridDim.x * kWarpsPerCta;
+    for (bool first = true;; first = false) {
+        int item = (int)blockIdx.x * kWarpsPerCta + (tid >> 5);
+        if (!first) {
+            if (lane == 0) item = atomicAdd(P.item_counter + parity, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+        }
+#if TEEFLOW_INTERLEAVE
+        if (item >= n_draws) break;
+        int lo, strip;
+        {
+            const int C = item / kChunk;
+            lo = C % P.S;
+            strip = (C / P.S) * kChunk + item % kChunk;
+        }
+        if (strip >= s_prefix[lo + 1] - s_prefix[lo]) continue;
+#else
         if (item >= total) break;
+#endif
 #else
     const int n_warps = gridDim.x * kWarpsPerCta;
     // CTA-interleaved item order: the 8 warps of a CTA take 8 consecutive strips (shared cache lines)
     for (int item = blockIdx.x * kWarpsPerCta + (tid >> 5); item < total; item += n_warps) {
 #endif
+#if !(TEEFLOW_DYNAMIC_ITEMS && TEEFLOW_INTERLEAVE)
         int lo = 0, hi = P.S;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] <= item) lo = mid; else hi = mid; }
-        const int slot = P.slot0 + lo;            // absolute slot: planes, arrival counter, partials
         const int strip = item - s_prefix[lo];
+#endif
+        const int slot = P.slot0 + lo;            // absolute slot: planes, arrival counter, partials
         const Slot* sp = cur + lo;
         const int pair = sp->pair, phase = sp->phase, level = sp->level, ucur = sp->ucur, pcur = sp->pcur;
         const int n_items = s_prefix[lo + 1] - s_prefix[lo];
 
         double err = 0.0, aux = 0.0;
         switch (phase) {
-            case PH_LEVEL_INIT: op_level_init(P, level, ucur, slot, strip, lane); break;
-            case PH_WARP: op_warp(P, level, ucur, pair, slot, strip, lane, s_cubic); break;
-            case PH_MEDIAN: op_median(P, level, ucur, slot, strip, lane); break;
-            case PH_INNER: err = op_inner(P, level, ucur, pcur, slot, strip, lane); break;
-            case PH_WASE: op_wase(P, ucur, slot, strip, lane, err, aux); break;
-            case PH_FINAL: op_final(P, ucur, pair, sp->bg, slot, strip, lane); break;
+            case PH_LEVEL_INIT: op_level_init<PITCH>(P, level, ucur, slot, strip, lane); break;
+            case PH_WARP: op_warp<PITCH>(P, level, ucur, pair, slot, strip, lane, s_cubic); break;
+            case PH_MEDIAN: op_median<PITCH>(P, level, ucur, slot, strip, lane); break;
+            case PH_INNER: err = op_inner<PITCH>(P, level, ucur, pcur, slot, strip, lane); break;
+            case PH_WASE: op_wase<PITCH>(P, ucur, slot, strip, lane, err, aux); break;
+            case PH_FINAL: op_final<PITCH>(P, ucur, pair, sp->bg, slot, strip, lane); break;
             default: break;
         }
         __syncwarp();
