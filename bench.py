@@ -150,6 +150,40 @@ def run_reference_arm(args):
     return 0
 
 
+def phase_probe(frames_dev, device):
+    """Per-phase throughput of the strip ops at full resolution (see the call site).  Bytes per pixel are the
+    algorithmic figures of SURVEY.md 8d: inner 64, median 16, warp 32, level-init (coarsest: writes u, p) 24."""
+    import numpy as np
+    from tee_optical_flow_b200.engine import TVL1Engine
+    peak, _ = measured_peak()
+    old = os.environ.get("TEEFLOW_GROUPS")
+    os.environ["TEEFLOW_GROUPS"] = "1"
+    try:
+        eng = TVL1Engine(device=device, nscales=1, warps=1, max_slots=frames_dev.shape[0] - 1)
+    finally:
+        if old is None:
+            os.environ.pop("TEEFLOW_GROUPS", None)
+        else:
+            os.environ["TEEFLOW_GROUPS"] = old
+    n, Hh, Ww = frames_dev.shape
+    px = (n - 1) * Hh * Ww
+    eng.time_launches(12)
+    ms = None
+    for _ in range(3):
+        eng._calc_clip_device(frames_dev, 1.0, True, False, True)
+        t = eng.launch_times_ms()
+        ms = t if ms is None else np.minimum(ms, t[:len(ms)])
+    eng.close()
+    inner_ms = float(np.median(ms[3:9]))
+    out = {"what": "63 pairs x 600x800 px per launch, one pyramid level, lockstep launches (best of 3 runs)",
+           "px_per_launch": px}
+    for name, t, b in (("level_init", float(ms[0]), 24), ("warp", float(ms[1]), 32), ("median", float(ms[2]), 16),
+                       ("inner", inner_ms, 64)):
+        gbs = px * b / (t * 1e-3) / 1e9
+        out[name] = {"ms": t, "bytes_per_px": b, "algorithmic_GBps": gbs, "frac_of_peak": gbs / peak}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -268,6 +302,16 @@ def main():
     except Exception as e:  # informational only
         analysis = {"error": str(e)[:200]}
 
+    # ---- per-phase roofline (rank 0, informational): the step kernel runs four different strip ops; with one slot
+    # group and ONE pyramid level all 63 pairs step in lockstep at first, so launch 0 is a pure level-init, 1 a pure
+    # warp, 2 a pure median and 3.. pure inner iterations over 63 x 600 x 800 px -- timed with CUDA events per launch
+    phases = None
+    if rank == 0:
+        try:
+            phases = phase_probe(frames_dev, local_rank)
+        except Exception as e:  # informational only
+            phases = {"error": str(e)[:200]}
+
     t_max = torch.tensor([dev_s, wall_s, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
@@ -315,6 +359,7 @@ def main():
                          "solver_share_of_step": solver_ms / 1e3 / step_s},
             "clocks": clocks,
             "analysis_config3": analysis,
+            "phase_roofline": phases,
         }
         if world == 1 and not args.no_cpu_baseline:
             sample_pairs = 6

@@ -128,6 +128,13 @@ typedef struct {
  * Returns the number of pairs of the last calc. */
 TEEFLOW_API int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap);
 TEEFLOW_API int teeflow_get_stats(teeflow_handle h, teeflow_stats* out);
+/* Diagnostics for the roofline accounting of the individual phases: time the first n (<= 64) solver launches of
+ * every following calc with CUDA events on the launching stream (n = 0 switches it off), and fetch the durations
+ * (ms) of the last calc.  With one slot group (environment TEEFLOW_GROUPS=1 at teeflow_create) and as many slots as
+ * pairs, all pairs step in lockstep at first, so launch 0 is a pure level-init, 1 a pure warp, 2 a pure median,
+ * 3.. pure inner iterations over all pairs.  teeflow_get_launch_times returns the number of launches timed. */
+TEEFLOW_API int teeflow_time_launches(teeflow_handle h, int n);
+TEEFLOW_API int teeflow_get_launch_times(teeflow_handle h, float* ms, int cap);
 
 /* Pyramid geometry the handle would use for an H x W image: level sizes (finest first). Returns the level count. */
 TEEFLOW_API int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws);

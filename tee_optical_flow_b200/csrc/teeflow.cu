@@ -89,6 +89,11 @@ struct teeflow_engine {
     int groups = 2;                                   // slot groups stepping on separate streams
     cudaStream_t group_stream[kMaxGroups - 1] = {};
     cudaEvent_t ev_group[2][kMaxGroups - 1] = {};
+    // per-launch timing diagnostics (teeflow_time_launches)
+    static const int kMaxLaunchEvents = 64;
+    int n_launch_events = 0, n_launches_timed = 0;
+    cudaEvent_t ev_launch[kMaxLaunchEvents + 1] = {};
+    float launch_ms[kMaxLaunchEvents] = {};
     // last-call record
     teeflow_stats st{};
 };
@@ -212,6 +217,7 @@ int teeflow_destroy(teeflow_handle h) {
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
     if (h->ev_tp) cudaEventDestroy(h->ev_tp);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (auto& ev : h->ev_launch) if (ev) cudaEventDestroy(ev);
     for (int g = 0; g < kMaxGroups - 1; ++g) {
         if (h->group_stream[g]) cudaStreamDestroy(h->group_stream[g]);
         for (int w = 0; w < 2; ++w) if (h->ev_group[w][g]) cudaEventDestroy(h->ev_group[w][g]);
@@ -257,6 +263,22 @@ int teeflow_get_param(teeflow_handle h, const char* key, double* value) {
     if (double* d = param_slot_d(h->p, key)) { *value = *d; return TEEFLOW_OK; }
     if (int32_t* i = param_slot_i(h->p, key)) { *value = (double)*i; return TEEFLOW_OK; }
     return fail(h, TEEFLOW_ERR_BAD_ARG, "unknown parameter '%s'", key);
+}
+
+int teeflow_time_launches(teeflow_handle h, int n) {
+    if (!h || n < 0 || n > teeflow_engine::kMaxLaunchEvents) return fail(h, TEEFLOW_ERR_BAD_ARG, "n must be in [0,%d]", teeflow_engine::kMaxLaunchEvents);
+    CU_TRY(h, cudaSetDevice(h->device));
+    for (int i = 0; i <= n && n > 0; ++i)
+        if (!h->ev_launch[i]) CU_TRY(h, cudaEventCreate(&h->ev_launch[i]));
+    h->n_launch_events = n;
+    h->n_launches_timed = 0;
+    return TEEFLOW_OK;
+}
+
+int teeflow_get_launch_times(teeflow_handle h, float* ms, int cap) {
+    if (!h || (!ms && cap > 0) || cap < 0) return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    for (int i = 0; i < h->n_launches_timed && i < cap; ++i) ms[i] = h->launch_ms[i];
+    return h->n_launches_timed;
 }
 
 int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs, int32_t* Ws) {
@@ -522,6 +544,13 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         h->st.kernel_launches = 1 + 2 * (long long)L - 1;
     }
 
+    // ---- launch geometry: G slot groups on G streams, persistent grid of resident CTAs
+    const int G = (S >= 2 * kMinGroupSlots && h->groups > 1) ? std::min(h->groups, kMaxGroups) : 1;
+    // every launch fills all resident CTA slots; giving each group 1/G of them, so that the groups' launches are
+    // co-resident on every SM all the time, was measured slower (1037 vs 1134 pairs/s): few slots at a time sweeping
+    // the same image rows keeps DRAM pages open
+    const int grid = h->num_sms * h->ctas_per_sm[pitch_i];
+
     // ---- slot table: the first S pairs start at the coarsest level, parity 0
     {
         std::vector<Slot> init((size_t)kMaxSlots);
@@ -536,7 +565,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         int ctl0[kCtlInts] = {0};
         ctl0[0] = S;
         // strip counters of launch parity 0: the first strip of a warp is its own index (tvl1_step_kernel)
-        for (int g = 0; g < kMaxGroups; ++g) ctl0[2 + 2 * g] = h->num_sms * h->ctas_per_sm[pitch_i] * kWarpsPerCta;
+        for (int g = 0; g < kMaxGroups; ++g) ctl0[2 + 2 * g] = grid * kWarpsPerCta;
         CU_TRY(h, cudaMemcpyAsync(h->ctl, ctl0, sizeof(ctl0), cudaMemcpyHostToDevice, stream));
         CU_TRY(h, cudaStreamSynchronize(stream));  // `init` / ctl0 / pair lists are host temporaries
         CU_TRY(h, cudaEventRecord(h->ev_tp, stream));
@@ -546,10 +575,8 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     // drains (its last strips, the launch gap, the next launch's prologue) the other group's strips keep the SMs
     // busy.  The host keeps two chunks of launches in flight per stream and polls the done counter of the chunk
     // before; finished slots make their warps exit at once, so an over-issued launch costs microseconds.
-    const int grid = h->num_sms * h->ctas_per_sm[pitch_i];
     const step_kernel_t step_kernel = step_kernel_for(pitch);
     const int chunk = 16;
-    const int G = (S >= 2 * kMinGroupSlots && h->groups > 1) ? std::min(h->groups, kMaxGroups) : 1;
     EngineParams Pg[kMaxGroups];
     cudaStream_t gs[kMaxGroups];
     for (int g = 0; g < G; ++g) {
@@ -565,14 +592,19 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     const long long max_steps = steps_per_pair * ((n_pairs + S - 1) / S + 1) * G + 2 * chunk;
     long long step = 0;
     int n_chunks = 0;
+    h->n_launches_timed = 0;
     bool done = false;
     volatile int* hd = h->h_done;
     hd[0] = hd[1] = 0;
     while (!done) {
         if (step > max_steps) return fail(h, TEEFLOW_ERR_STATE, "scheduler exceeded %lld steps", max_steps);
         for (int k = 0; k < chunk; ++k, ++step)
-            for (int g = 0; g < G; ++g)
+            for (int g = 0; g < G; ++g) {
+                const bool timed = g == 0 && step < h->n_launch_events;
+                if (timed && step == 0) CU_TRY(h, cudaEventRecord(h->ev_launch[0], gs[0]));
                 step_kernel<<<grid, kThreads, 0, gs[g]>>>(Pg[g], (int)(step & 1));
+                if (timed) { CU_TRY(h, cudaEventRecord(h->ev_launch[step + 1], gs[0])); h->n_launches_timed = (int)step + 1; }
+            }
         CU_TRY(h, cudaGetLastError());
         const int which = n_chunks & 1;
         // join the group streams into the caller's stream at the chunk boundary, then sample the done counter
@@ -599,6 +631,8 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         if (d < n_pairs) return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", d, n_pairs);
     }
     step *= G;
+    for (int i = 0; i < h->n_launches_timed; ++i)
+        CU_TRY(h, cudaEventElapsedTime(&h->launch_ms[i], h->ev_launch[i], h->ev_launch[i + 1]));
     CU_TRY(h, cudaEventElapsedTime(&h->st.device_ms, h->ev_t0, h->ev_t1));
     CU_TRY(h, cudaEventElapsedTime(&h->st.pyramid_ms, h->ev_t0, h->ev_tp));
     CU_TRY(h, cudaEventElapsedTime(&h->st.solver_ms, h->ev_tp, h->ev_t1));

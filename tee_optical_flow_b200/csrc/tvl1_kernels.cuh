@@ -26,13 +26,6 @@ constexpr int kPR = 8;         // pointwise strip: rows per warp (32 columns)
 #ifndef TEEFLOW_DYNAMIC_ITEMS
 #define TEEFLOW_DYNAMIC_ITEMS 1
 #endif
-#ifndef TEEFLOW_INTERLEAVE
-#define TEEFLOW_INTERLEAVE 0   // measured: slot-interleaved hand-out 1043-1053 pairs/s vs 1127 slot by slot (locality wins)
-#endif
-#ifndef TEEFLOW_CHUNK
-#define TEEFLOW_CHUNK 8
-#endif
-constexpr int kChunk = TEEFLOW_CHUNK;   // consecutive strips handed out together (they share halo cache lines)
 
 // ------------------------------------------------------------------------------------------------ pyramid
 // level 0: convertTo(CV_32F, 1) for u8, x255 for f32 (tvl1flow.cpp: I0mult / I1mult)
@@ -611,21 +604,6 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     }
     __syncthreads();
     const int total = s_prefix[P.S];
-#if TEEFLOW_INTERLEAVE
-    // Slot-interleaved hand-out: chunk C of kChunk consecutive strips -> slot C % S, chunk C / S of that slot.  At
-    // every moment the running warps work on ALL slots of the group (a few consecutive chunks of each, so the strips
-    // of one slot are still visited in raster order): the HBM-bound phase (inner) and the ALU-bound ones (median,
-    // warp) of different slots share every SM instead of alternating slot by slot.  Draws beyond a slot's last
-    // strip are skipped.
-    __shared__ int s_maxn;
-    if (tid == 0) {
-        int m = 0;
-        for (int q = 0; q < P.S; ++q) m = max(m, s_prefix[q + 1] - s_prefix[q]);
-        s_maxn = m;
-    }
-    __syncthreads();
-    const int n_draws = P.S * ((s_maxn + kChunk - 1) / kChunk) * kChunk;
-#endif
 
     // slots without work this step: carry their state over to the other parity unchanged
     if (blockIdx.x == 0)
@@ -634,7 +612,11 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
 
 #if TEEFLOW_DYNAMIC_ITEMS
     // dynamic distribution: every warp pulls the next strip from a per-launch counter, so strips of unequal cost
-    // (inner / median / warp phases mix in one launch) balance out; the counter of the other parity is re-armed
+    // (inner / median / warp phases mix in one launch) balance out; the counter of the other parity is re-armed.
+    // Strips are handed out slot by slot in raster order: at any moment the running warps work on neighbouring
+    // strips of very few slots and sweep the same image rows together, which is what keeps DRAM pages open --
+    // handing out strips interleaved over the slots of the group (so that the ALU-bound median / warp strips of
+    // some slots overlap the HBM-bound inner strips of others) was measured at 897-1053 pairs/s against 1134.
     // The first strip of every warp is its global warp index (no burst of same-address atomics at launch); the
     // counter therefore starts at the number of warps of the grid.
     if (blockIdx.x == 0 && tid == 0) P.item_counter[parity ^ 1] = (int)gridDim.x * kWarpsPerCta;
@@ -644,28 +626,15 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
             if (lane == 0) item = atomicAdd(P.item_counter + parity, 1);
             item = __shfl_sync(0xffffffffu, item, 0);
         }
-#if TEEFLOW_INTERLEAVE
-        if (item >= n_draws) break;
-        int lo, strip;
-        {
-            const int C = item / kChunk;
-            lo = C % P.S;
-            strip = (C / P.S) * kChunk + item % kChunk;
-        }
-        if (strip >= s_prefix[lo + 1] - s_prefix[lo]) continue;
-#else
         if (item >= total) break;
-#endif
 #else
     const int n_warps = gridDim.x * kWarpsPerCta;
     // CTA-interleaved item order: the 8 warps of a CTA take 8 consecutive strips (shared cache lines)
     for (int item = blockIdx.x * kWarpsPerCta + (tid >> 5); item < total; item += n_warps) {
 #endif
-#if !(TEEFLOW_DYNAMIC_ITEMS && TEEFLOW_INTERLEAVE)
         int lo = 0, hi = P.S;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] <= item) lo = mid; else hi = mid; }
         const int strip = item - s_prefix[lo];
-#endif
         const int slot = P.slot0 + lo;            // absolute slot: planes, arrival counter, partials
         const Slot* sp = cur + lo;
         const int pair = sp->pair, phase = sp->phase, level = sp->level, ucur = sp->ucur, pcur = sp->pcur;

@@ -361,6 +361,15 @@ class TVL1Engine:
         info = {k: getattr(st, k) for k, _ in _lib.TeeflowStats._fields_ if k != "reserved"}
         return buf[:n, :st.n_levels].copy(), info
 
+    def time_launches(self, n: int) -> None:
+        """Diagnostics: time the first n solver launches of every following calc (teeflow_time_launches)."""
+        self._check(self._lib.teeflow_time_launches(self._h, int(n)))
+
+    def launch_times_ms(self) -> np.ndarray:
+        buf = (C.c_float * 64)()
+        n = self._check(self._lib.teeflow_get_launch_times(self._h, buf, 64))
+        return np.array(buf[:n], np.float32)
+
     def level_sizes(self, H: int, W: int):
         hs = (C.c_int32 * _lib.TEEFLOW_MAX_LEVELS)()
         ws = (C.c_int32 * _lib.TEEFLOW_MAX_LEVELS)()
