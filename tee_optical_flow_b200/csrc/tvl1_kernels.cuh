@@ -218,24 +218,40 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
     const int x = (strip % g.pw_sx) * 32 + lane;
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
+    if (P.median == 5) {
+        // two output rows per step: their windows share rows y-1 .. y+2 (median25_pair); one flow channel at a time
+        // (the 30 values of a channel are re-read from L1 for the second one: registers, not loads, are scarce here)
+        const float* Uf = reinterpret_cast<const float*>(SB);
+        int xs[5];
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) xs[dx] = clampi(x + dx - 2, 0, g.W - 1);
+        for (int y = y0; y < y1; y += 2) {
+            unsigned ro[6];       // element offsets of rows y-2 .. y+3 (BORDER_REPLICATE)
+#pragma unroll
+            for (int r = 0; r < 6; ++r) ro[r] = L::at(pUs, clampi(y + r - 2, 0, g.H - 1), 0);
+            float2 top, bot;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float sh[20], tp[5], bt[5];
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx) {
+                    tp[dx] = __ldg(Uf + 2 * (ro[0] + (unsigned)xs[dx]) + ch);
+                    bt[dx] = __ldg(Uf + 2 * (ro[5] + (unsigned)xs[dx]) + ch);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) sh[r * 5 + dx] = __ldg(Uf + 2 * (ro[r + 1] + (unsigned)xs[dx]) + ch);
+                }
+                float mt, mb;
+                median25_pair(sh, tp, bt, mt, mb);
+                if (ch == 0) { top.x = mt; bot.x = mb; } else { top.y = mt; bot.y = mb; }
+            }
+            SB[L::at(pUd, y, x)] = top;
+            if (y + 1 < y1) SB[L::at(pUd, y + 1, x)] = bot;
+        }
+        return;
+    }
     for (int y = y0; y < y1; ++y) {
         float2 out;
-        if (P.median == 5) {
-            float v[25], w[25];
-#pragma unroll
-            for (int dy = -2; dy <= 2; ++dy) {
-                const int yy = clampi(y + dy, 0, g.H - 1);
-#pragma unroll
-                for (int dx = -2; dx <= 2; ++dx) {
-                    const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = __ldg(SB + L::at(pUs, yy, xx));
-                    v[(dy + 2) * 5 + dx + 2] = t.x;
-                    w[(dy + 2) * 5 + dx + 2] = t.y;
-                }
-            }
-            out.x = median25(v);
-            out.y = median25(w);
-        } else {
+        {
             float v[9], w[9];
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
