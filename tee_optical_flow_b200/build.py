@@ -18,7 +18,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libteeflow.so"
 SOURCES = [CSRC / "teeflow.cu"]
-HEADERS = [CSRC / "tvl1_device.cuh", CSRC / "tvl1_kernels.cuh", CSRC / "finalize_kernels.cuh",
+HEADERS = [CSRC / "tvl1_device.cuh", CSRC / "tvl1_kernels.cuh", CSRC / "finalize_kernels.cuh", CSRC / "median_networks.inc",
            PKG.parent / "include" / "teeflow.h"]
 
 NVCC_FLAGS = [

@@ -219,33 +219,43 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
     const int y0 = (strip / g.pw_sx) * kPR, y1 = min(y0 + kPR, g.H);
     if (x >= g.W) return;
     if (P.median == 5) {
-        // two output rows per step: their windows share rows y-1 .. y+2 (median25_pair); one flow channel at a time
-        // (the 30 values of a channel are re-read from L1 for the second one: registers, not loads, are scarce here)
+        // sorted-row walk (tvl1_device.cuh): two output rows per step, one flow channel at a time (the rolling
+        // state of a channel is 25 registers)
         const float* Uf = reinterpret_cast<const float*>(SB);
-        int xs[5];
+        float* Uw = reinterpret_cast<float*>(SB);
+        unsigned xs[5];
 #pragma unroll
-        for (int dx = 0; dx < 5; ++dx) xs[dx] = clampi(x + dx - 2, 0, g.W - 1);
-        for (int y = y0; y < y1; y += 2) {
-            unsigned ro[6];       // element offsets of rows y-2 .. y+3 (BORDER_REPLICATE)
+        for (int dx = 0; dx < 5; ++dx) xs[dx] = 2u * (unsigned)clampi(x + dx - 2, 0, g.W - 1);
+#pragma unroll 1
+        for (unsigned ch = 0; ch < 2; ++ch) {
+            auto load_sorted = [&](int yy, float* v) {   // sorted 5-tuple of row yy (BORDER_REPLICATE) around x
+                const float* row = Uf + (2u * L::at(pUs, clampi(yy, 0, g.H - 1), 0) + ch);
 #pragma unroll
-            for (int r = 0; r < 6; ++r) ro[r] = L::at(pUs, clampi(y + r - 2, 0, g.H - 1), 0);
-            float2 top, bot;
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                float sh[20], tp[5], bt[5];
-#pragma unroll
-                for (int dx = 0; dx < 5; ++dx) {
-                    tp[dx] = __ldg(Uf + 2 * (ro[0] + (unsigned)xs[dx]) + ch);
-                    bt[dx] = __ldg(Uf + 2 * (ro[5] + (unsigned)xs[dx]) + ch);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) sh[r * 5 + dx] = __ldg(Uf + 2 * (ro[r + 1] + (unsigned)xs[dx]) + ch);
-                }
-                float mt, mb;
-                median25_pair(sh, tp, bt, mt, mb);
-                if (ch == 0) { top.x = mt; bot.x = mb; } else { top.y = mt; bot.y = mb; }
+                for (int dx = 0; dx < 5; ++dx) v[dx] = __ldg(row + xs[dx]);
+                TF_MED_SORT5(v)
+            };
+            float T[5], S0[5], N1[5], Pp[10];
+            {
+                float a[5];
+                load_sorted(y0 - 2, T);
+                load_sorted(y0 - 1, a);
+                load_sorted(y0, S0);
+                med_merge55(a, S0, Pp);
+                load_sorted(y0 + 1, N1);
             }
-            SB[L::at(pUd, y, x)] = top;
-            if (y + 1 < y1) SB[L::at(pUd, y + 1, x)] = bot;
+            for (int y = y0; y < y1; y += 2) {
+                float N2[5], B[5], Pn[10], mid[6];
+                load_sorted(y + 2, N2);
+                load_sorted(y + 3, B);
+                med_merge55(N1, N2, Pn);
+                med_mid6(Pp, Pn, mid);
+                Uw[2u * L::at(pUd, y, x) + ch] = med_finish(mid, T);
+                if (y + 1 < y1) Uw[2u * L::at(pUd, y + 1, x) + ch] = med_finish(mid, B);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { T[i] = S0[i]; S0[i] = N2[i]; N1[i] = B[i]; }
+#pragma unroll
+                for (int i = 0; i < 10; ++i) Pp[i] = Pn[i];
+            }
         }
         return;
     }

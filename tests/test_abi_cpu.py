@@ -102,3 +102,14 @@ def test_synth_is_deterministic():
     m = make_masks(3, 3, 48, 64)
     assert set(m) == {"rv", "av", "bkgd"} and m["rv"].shape == (3, 48, 64, 2) and m["rv"].dtype == bool
     assert not np.any(m["bkgd"] & (m["rv"] | m["av"]))
+
+
+def test_median_networks_are_verified_and_current():
+    """the compare-exchange networks of the 5x5 median (sorted rows, shared middle six) select the median of every
+    zero-one window (2^25 cases => every input, 0-1 principle) and median_networks.inc is what the generator emits"""
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, str(ROOT / "tools" / "gen_median_networks.py"), "--check"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "wrong medians over 2^25 zero-one windows: 0" in res.stdout
