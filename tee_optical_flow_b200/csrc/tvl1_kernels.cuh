@@ -17,12 +17,18 @@ namespace teeflow {
 
 constexpr int kThreads = 256;  // threads per CTA
 constexpr int kWarpsPerCta = kThreads / 32;
-constexpr int kIW = 31;        // inner strip: output columns per warp (lane 31 = right halo column)
-#ifndef TEEFLOW_STRIP_ROWS
-#define TEEFLOW_STRIP_ROWS 16
+#ifndef TEEFLOW_IW
+#define TEEFLOW_IW 31
 #endif
-constexpr int kIR = TEEFLOW_STRIP_ROWS;   // inner strip: rows per warp (16 beats 32 / 24 / 12 / 8 with dynamic strip hand-out)
-constexpr int kPR = 8;         // pointwise strip: rows per warp (32 columns)
+constexpr int kIW = TEEFLOW_IW;        // inner strip: output columns per warp (lane 31 = right halo column)
+#ifndef TEEFLOW_STRIP_ROWS
+#define TEEFLOW_STRIP_ROWS 20
+#endif
+constexpr int kIR = TEEFLOW_STRIP_ROWS;   // inner strip: rows per warp (measured 16: 1215, 20: 1245, 24: 1241, 32: 1233, 40: 1200 pairs/s)
+#ifndef TEEFLOW_POINT_ROWS
+#define TEEFLOW_POINT_ROWS 16
+#endif
+constexpr int kPR = TEEFLOW_POINT_ROWS;   // pointwise strip: rows per warp, 32 columns (measured 8: 1243, 12: 1250, 16: 1264, 24: 1244 pairs/s)
 #ifndef TEEFLOW_DYNAMIC_ITEMS
 #define TEEFLOW_DYNAMIC_ITEMS 1
 #endif
