@@ -232,12 +232,19 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
         unsigned xs[5];
 #pragma unroll
         for (int dx = 0; dx < 5; ++dx) xs[dx] = 2u * (unsigned)clampi(x + dx - 2, 0, g.W - 1);
+        const bool interior = x >= 2 && x + 2 < g.W;
 #pragma unroll 1
         for (unsigned ch = 0; ch < 2; ++ch) {
             auto load_sorted = [&](int yy, float* v) {   // sorted 5-tuple of row yy (BORDER_REPLICATE) around x
                 const float* row = Uf + (2u * L::at(pUs, clampi(yy, 0, g.H - 1), 0) + ch);
+                if (interior) {                          // x-2 .. x+2 inside the image: one pointer + immediates
+                    const float* q = row + xs[0];
 #pragma unroll
-                for (int dx = 0; dx < 5; ++dx) v[dx] = __ldg(row + xs[dx]);
+                    for (int dx = 0; dx < 5; ++dx) v[dx] = __ldg(q + 2 * dx);
+                } else {
+#pragma unroll
+                    for (int dx = 0; dx < 5; ++dx) v[dx] = __ldg(row + xs[dx]);
+                }
                 TF_MED_SORT5(v)
             };
             float T[5], S0[5], N1[5], Pp[10];

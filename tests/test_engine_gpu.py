@@ -56,7 +56,8 @@ def test_golden_pairs_bitexact(pairs, case):
     assert _epe(flow, pairs[f"{case}__flow_em0"]).mean() <= EPE_TOL
 
 
-@pytest.mark.parametrize("shape", [(16, 16), (17, 23), (33, 65), (64, 64), (65, 129), (100, 37)])
+@pytest.mark.parametrize("shape", [(16, 16), (17, 23), (33, 65), (64, 64), (65, 129), (100, 37),
+                                   (24, 1100), (20, 2100)])   # the last two: plane pitch 2048 / 4096
 def test_ragged_sizes_vs_oracle(oracle, shape):
     """tile-boundary cases: sizes below / at / just above the 64x16 tile, odd sizes, pyramid stop < 16 px"""
     from tee_optical_flow_b200.synth import make_clip
