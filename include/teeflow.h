@@ -120,6 +120,8 @@ typedef struct {
     float pyramid_ms;         /* pyramid + gradient pack kernels */
     float solver_ms;          /* first to last solver launch */
     float reserved;
+    int32_t double_steps;            /* two-iteration passes of the inner loop that were applied ... */
+    int32_t double_steps_discarded;  /* ... and discarded (the first iteration already met the exit test) */
 } teeflow_stats;
 
 /* Work actually executed by the last calc: counters[p][level][3] = inner iterations, median passes, warps

@@ -32,6 +32,7 @@ class TeeflowStats(C.Structure):
         ("n_pairs", C.c_int32), ("n_levels", C.c_int32), ("n_slots", C.c_int32), ("grid_ctas", C.c_int32),
         ("solver_launches", C.c_int64), ("kernel_launches", C.c_int64), ("device_ms", C.c_float),
         ("pyramid_ms", C.c_float), ("solver_ms", C.c_float), ("reserved", C.c_float),
+        ("double_steps", C.c_int32), ("double_steps_discarded", C.c_int32),
     ]
 
 

@@ -25,10 +25,11 @@ static_assert(TEEFLOW_MAX_LEVELS == kMaxLevels, "ABI level count");
 static thread_local std::string g_last_error;
 static const int kMaxGroups = 4;        // slot groups (streams) per handle
 static const int kMinGroupSlots = 4;    // do not split fewer than 2 * this many slots
-static const int kCtlInts = 2 + 2 * kMaxGroups;   // next_pair, pairs_done, per-group item counters [parity]
+static const int kCtlInts = 2 + 2 * kMaxGroups + 2;   // next_pair, pairs_done, per-group item counters [parity], two-iteration stats
 #ifndef TEEFLOW_PITCH0
 #define TEEFLOW_PITCH0 1024
 #endif
+static const size_t kRingSmem = (size_t)kWarpsPerCta * kRingB;   // dynamic shared memory of a launch with two-iteration strips
 static const int kPitches[] = {TEEFLOW_PITCH0, 2048, 4096};  // instantiated plane pitches (float2 elements): W <= pitch
 static const size_t kPlaneAlign = (size_t)kPlanes * 4096 * sizeof(float2);   // Lay<4096>::ROWB, a multiple of the others
 
@@ -47,6 +48,7 @@ struct teeflow_engine {
     int device = 0;
     int num_sms = 0;
     int ctas_per_sm[3] = {1, 1, 1};   // per instantiated pitch
+    int ctas_per_sm_ring[3] = {1, 1, 1};   // ... with the two-iteration strips' shared-memory ring
     std::string err;
     // workspace (grown on demand)
     size_t cap_frames = 0, cap_pyr_stride = 0;
@@ -87,6 +89,7 @@ struct teeflow_engine {
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_tp = nullptr;
     cudaStream_t own_stream = nullptr;
     int groups = 2;                                   // slot groups stepping on separate streams
+    float spec_factor = 0.0f;                         // two-iteration passes while error > spec_factor * threshold (0: off)
     cudaStream_t group_stream[kMaxGroups - 1] = {};
     cudaEvent_t ev_group[2][kMaxGroups - 1] = {};
     // per-launch timing diagnostics (teeflow_time_launches)
@@ -182,6 +185,8 @@ int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
         CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_for(kPitches[i]), kThreads, 0));
         if (occ < 1) { delete h; return fail(nullptr, TEEFLOW_ERR_CUDA, "tvl1_step_kernel cannot be resident on this device"); }
         h->ctas_per_sm[i] = occ;
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_for(kPitches[i]), kThreads, kRingSmem));
+        h->ctas_per_sm_ring[i] = std::max(occ, 1);
     }
     CU_TRY(h, cudaMallocHost(&h->h_done, sizeof(int) * 4));
     CU_TRY(h, cudaMalloc(&h->ctl, sizeof(int) * kCtlInts));
@@ -195,6 +200,7 @@ int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
         for (int w = 0; w < 2; ++w) CU_TRY(h, cudaEventCreateWithFlags(&h->ev_group[w][g], cudaEventDisableTiming));
     }
     if (const char* e = getenv("TEEFLOW_GROUPS")) h->groups = std::max(1, std::min(atoi(e), kMaxGroups));
+    if (const char* e = getenv("TEEFLOW_SPEC")) h->spec_factor = std::max(0.0f, (float)atof(e));
     *out = h;
     return TEEFLOW_OK;
 }
@@ -227,6 +233,7 @@ int teeflow_destroy(teeflow_handle h) {
 }
 
 static double* param_slot_d(teeflow_params& p, const char* key) {
+    if (!strcmp(key, "spec_factor")) return nullptr;   // handle-level knob, see teeflow_set_param
     if (!strcmp(key, "tau")) return &p.tau;
     if (!strcmp(key, "lambda")) return &p.lambda;
     if (!strcmp(key, "theta")) return &p.theta;
@@ -246,6 +253,11 @@ static int32_t* param_slot_i(teeflow_params& p, const char* key) {
 
 int teeflow_set_param(teeflow_handle h, const char* key, double value) {
     if (!h || !key) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL handle or key");
+    if (!strcmp(key, "spec_factor")) {   // two-iteration passes of the inner loop (0: off); results never depend on it
+        if (!(value >= 0)) return fail(h, TEEFLOW_ERR_BAD_ARG, "spec_factor must be >= 0");
+        h->spec_factor = (float)value;
+        return TEEFLOW_OK;
+    }
     teeflow_params np = h->p;
     if (double* d = param_slot_d(np, key)) *d = value;
     else if (int32_t* i = param_slot_i(np, key)) {
@@ -260,6 +272,7 @@ int teeflow_set_param(teeflow_handle h, const char* key, double value) {
 
 int teeflow_get_param(teeflow_handle h, const char* key, double* value) {
     if (!h || !key || !value) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
+    if (!strcmp(key, "spec_factor")) { *value = h->spec_factor; return TEEFLOW_OK; }
     if (double* d = param_slot_d(h->p, key)) { *value = *d; return TEEFLOW_OK; }
     if (int32_t* i = param_slot_i(h->p, key)) { *value = (double)*i; return TEEFLOW_OK; }
     return fail(h, TEEFLOW_ERR_BAD_ARG, "unknown parameter '%s'", key);
@@ -475,6 +488,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         g.H = Hs[l]; g.W = Ws[l];
         g.in_sx = (g.W + kIW - 1) / kIW; g.in_items = g.in_sx * ((g.H + kIR - 1) / kIR);
         g.pw_sx = (g.W + 31) / 32; g.pw_items = g.pw_sx * ((g.H + kPR - 1) / kPR);
+        g.in2_sx = (g.W + kIW2 - 1) / kIW2; g.in2_items = g.in2_sx * ((g.H + kIR2 - 1) / kIR2);
         g.pyr_off = off;
         off += ((long long)g.H * g.W + 63) / 64 * 64;
         g.scaled_eps = (float)(h->p.epsilon * h->p.epsilon * (double)(g.H * g.W));
@@ -496,7 +510,8 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     P.frame_pyr_stride = off;
     P.pitch = pitch;
     P.slot_stride = (long long)(H + 2) * kPlanes * pitch;   // two pad rows: the inner iteration's look-ahead loads
-    P.max_tiles = std::max(P.lv[0].in_items, 2 * P.lv[0].pw_items);
+    P.max_tiles = std::max(std::max(P.lv[0].in_items, 2 * P.lv[0].in2_items), 2 * P.lv[0].pw_items);
+    P.spec_factor = h->p.inner_iterations >= 2 ? h->spec_factor : 0.0f;
     if (h->wase_w && (h->wase_H != H || h->wase_W != W))
         return fail(h, TEEFLOW_ERR_BAD_SHAPE, "WASE weight map is %dx%d but the frames are %dx%d", h->wase_H, h->wase_W, H, W);
 
@@ -507,6 +522,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     P.planes = h->planes;
     P.arrive = h->arrive; P.partial = h->partial;
     P.next_pair = h->ctl; P.pairs_done = h->ctl + 1; P.item_counter = h->ctl + 2;
+    P.spec_stats = h->ctl + 2 + 2 * kMaxGroups;
     P.pair_a = h->pair_lists; P.pair_b = h->pair_lists + h->cap_pairs;
     P.out_index = h->pair_lists + 2 * h->cap_pairs; P.dup_index = h->pair_lists + 3 * h->cap_pairs;
     P.counters_out = h->counters;
@@ -549,7 +565,11 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     // every launch fills all resident CTA slots; giving each group 1/G of them, so that the groups' launches are
     // co-resident on every SM all the time, was measured slower (1037 vs 1134 pairs/s): few slots at a time sweeping
     // the same image rows keeps DRAM pages open
-    const int grid = h->num_sms * h->ctas_per_sm[pitch_i];
+    // two-iteration strips stage their rows in dynamic shared memory; launches without them take none, so the
+    // other phases keep the whole L1 (their spills and gathers live there)
+    const bool ring = P.spec_factor > 0.0f;
+    const size_t smem = ring ? kRingSmem : 0;
+    const int grid = h->num_sms * (ring ? h->ctas_per_sm_ring[pitch_i] : h->ctas_per_sm[pitch_i]);
 
     // ---- slot table: the first S pairs start at the coarsest level, parity 0
     {
@@ -576,6 +596,9 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     // busy.  The host keeps two chunks of launches in flight per stream and polls the done counter of the chunk
     // before; finished slots make their warps exit at once, so an over-issued launch costs microseconds.
     const step_kernel_t step_kernel = step_kernel_for(pitch);
+    CU_TRY(h, cudaFuncSetAttribute(step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   ring ? (int)((grid / h->num_sms) * (kRingSmem + 4096) * 100 / (228 * 1024)) + 1
+                                        : (int)cudaSharedmemCarveoutDefault));
     const int chunk = 16;
     EngineParams Pg[kMaxGroups];
     cudaStream_t gs[kMaxGroups];
@@ -602,7 +625,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
             for (int g = 0; g < G; ++g) {
                 const bool timed = g == 0 && step < h->n_launch_events;
                 if (timed && step == 0) CU_TRY(h, cudaEventRecord(h->ev_launch[0], gs[0]));
-                step_kernel<<<grid, kThreads, 0, gs[g]>>>(Pg[g], (int)(step & 1));
+                step_kernel<<<grid, kThreads, smem, gs[g]>>>(Pg[g], (int)(step & 1));
                 if (timed) { CU_TRY(h, cudaEventRecord(h->ev_launch[step + 1], gs[0])); h->n_launches_timed = (int)step + 1; }
             }
         CU_TRY(h, cudaGetLastError());
@@ -636,6 +659,11 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     CU_TRY(h, cudaEventElapsedTime(&h->st.device_ms, h->ev_t0, h->ev_t1));
     CU_TRY(h, cudaEventElapsedTime(&h->st.pyramid_ms, h->ev_t0, h->ev_tp));
     CU_TRY(h, cudaEventElapsedTime(&h->st.solver_ms, h->ev_tp, h->ev_t1));
+    {
+        int sp[2] = {0, 0};
+        CU_TRY(h, cudaMemcpy(sp, h->ctl + 2 + 2 * kMaxGroups, sizeof(sp), cudaMemcpyDeviceToHost));
+        h->st.double_steps = sp[0]; h->st.double_steps_discarded = sp[1];
+    }
     h->st.solver_launches = step;
     h->st.kernel_launches += step;
     h->st.n_slots = S;

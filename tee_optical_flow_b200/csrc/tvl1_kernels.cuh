@@ -25,6 +25,19 @@ constexpr int kIW = TEEFLOW_IW;        // inner strip: output columns per warp (
 #define TEEFLOW_STRIP_ROWS 20
 #endif
 constexpr int kIR = TEEFLOW_STRIP_ROWS;   // inner strip: rows per warp (measured 16: 1215, 20: 1245, 24: 1241, 32: 1233, 40: 1200 pairs/s)
+constexpr int kIW2 = 28;       // two-iteration strip: output columns per warp (lanes 1..28; lane 0 / 29 / 30 halo columns)
+#ifndef TEEFLOW_STRIP2_ROWS
+#define TEEFLOW_STRIP2_ROWS 24
+#endif
+constexpr int kIR2 = TEEFLOW_STRIP2_ROWS;   // two-iteration strip: rows per warp (3 extra rows are computed per strip)
+#ifndef TEEFLOW_RING2
+#define TEEFLOW_RING2 4
+#endif
+constexpr int kRing2 = TEEFLOW_RING2;       // image rows staged per warp (shared-memory ring): rows r-1, r + look-ahead
+constexpr int kSegPx = 34;                  // staged columns per plane row: [x0 - 2, x0 + 32)
+constexpr int kSegB = kSegPx * 8;           // 272 bytes = 17 x 16-byte copies
+constexpr int kStageB = 5 * kSegB;          // U, CA, CB, PX, PY of one image row
+constexpr int kRingB = kRing2 * kStageB;    // per warp
 #ifndef TEEFLOW_POINT_ROWS
 #define TEEFLOW_POINT_ROWS 16
 #endif
@@ -87,7 +100,12 @@ __global__ void pyr_pack_kernel(const float* __restrict__ pyrI, float4* __restri
 
 // ------------------------------------------------------------------------------------------- state machine
 // Control flow of OpticalFlowDual_TVL1::procOneScale / ::calc, one transition per finished phase.
-__device__ inline void advance_slot(const EngineParams& P, Slot& s, double err_sum) {
+// Two iterations per pass (PH_INNER2) are speculative: OpenCV tests the exit condition after EVERY iteration.  The
+// pass returns both error sums; if the first iteration already ends the loop, the pass is discarded (its inputs
+// are intact: it wrote the ping-pong partners) and that iteration is redone alone -- results never depend on the
+// choice, only the time does.  A pass is tried from the second iteration of a loop on, while the last error is
+// above spec_factor x the exit threshold (the error shrinks by less than that per iteration).
+__device__ inline void advance_slot(const EngineParams& P, Slot& s, double err_sum, double err_sum2) {
     const float eps = P.lv[s.level].scaled_eps;
     enum { NONE, CHECK_INNER, CHECK_OUTER, NEXT_WARP } todo = NONE;
     switch (s.phase) {
@@ -105,11 +123,27 @@ __device__ inline void advance_slot(const EngineParams& P, Slot& s, double err_s
             s.cnt[s.level][0]++;
             s.ucur ^= 1; s.pcur ^= 1;
             s.error = (float)err_sum; s.n_inner++; todo = CHECK_INNER; break;
+        case PH_INNER2: {
+            const float e1 = (float)err_sum;
+            if (!(e1 > eps && s.n_inner + 1 < P.inner)) {        // the loop ends after the first iteration
+                atomicAdd(P.spec_stats + 1, 1);
+                s.force_single = 1; s.phase = PH_INNER; return;
+            }
+            atomicAdd(P.spec_stats, 1);
+            s.cnt[s.level][0] += 2;
+            s.ucur ^= 1; s.pcur ^= 1;                            // the results sit in the partner planes
+            s.error = (float)err_sum2; s.n_inner += 2; todo = CHECK_INNER; break;
+        }
         default: return;
     }
     for (;;) {
         if (todo == CHECK_INNER) {
-            if (s.error > eps && s.n_inner < P.inner) { s.phase = PH_INNER; return; }
+            if (s.error > eps && s.n_inner < P.inner) {
+                const bool two = !s.force_single && s.n_inner >= 1 && s.n_inner + 2 <= P.inner &&
+                                 P.spec_factor > 0.f && s.error > P.spec_factor * eps;
+                s.force_single = 0;
+                s.phase = two ? PH_INNER2 : PH_INNER; return;
+            }
             s.n_outer++; todo = CHECK_OUTER;
         }
         if (todo == CHECK_OUTER) {
@@ -130,13 +164,14 @@ __device__ inline void advance_slot(const EngineParams& P, Slot& s, double err_s
 
 __device__ inline void start_pair(const EngineParams& P, Slot& s, int pair) {
     s.pair = pair; s.phase = PH_LEVEL_INIT; s.level = P.L - 1; s.warp = 0; s.n_outer = 0; s.n_inner = 0;
-    s.ucur = 0; s.pcur = 0; s.error = FLT_MAX; s.bg = 0.f;
+    s.ucur = 0; s.pcur = 0; s.error = FLT_MAX; s.bg = 0.f; s.force_single = 0;
     for (int l = 0; l < kMaxLevels; ++l) { s.cnt[l][0] = 0; s.cnt[l][1] = 0; s.cnt[l][2] = 0; }
 }
 
 __device__ __forceinline__ int items_of(const EngineParams& P, int phase, int pair, int level) {
     if (phase == PH_IDLE || pair < 0) return 0;
     if (phase == PH_FINAL || phase == PH_WASE) return P.lv[0].pw_items;
+    if (phase == PH_INNER2) return P.lv[level].in2_items;
     return phase == PH_INNER ? P.lv[level].in_items : P.lv[level].pw_items;
 }
 
@@ -554,6 +589,162 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     return err;
 }
 
+// ---- asynchronous staging (LDGSTS): 16 bytes per lane, global -> shared, bypassing L1 and the register file
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// PH_INNER2: TWO primal-dual iterations in one pass over the state (temporal blocking): 40 bytes read and 24
+// written per pixel for two iterations instead of one.  A warp owns kIW2 = 28 output columns and kIR2 rows; its 32
+// lanes sit on columns x0-1 .. x0+30 and it walks rows y0-1 .. y1+1, a four-stage software pipeline per row r:
+//   A(r)   u'  = first-iteration  u of row r        (all lanes)          needs p(r), p(r-1), u(r), coefficients(r)
+//   B(r-1) p'  = first-iteration  p of row r-1      (lanes 0..30)        needs u'(r-1), u'(r)
+//   C(r-1) u'' = second-iteration u of row r-1      (lanes 1..30)        needs u'(r-1), p'(r-1), p'(r-2), coeff.(r-1)
+//   D(r-2) p'' = second-iteration p of row r-2      (lanes 1..29)        needs u''(r-2), u''(r-1), p'(r-2)
+// Only u'(r-1), p'(r-1 / r-2) and u''(r-2) are carried in registers; the input rows live in a per-warp ring of
+// shared memory filled two rows ahead by 16-byte asynchronous copies, so rows r and r-1 are read where needed
+// instead of being kept.  Image borders follow the single-iteration rules in BOTH iterations; halo lanes outside
+// the image compute on whatever the margins hold and are masked where a neighbour reads them.  Error sums of both
+// iterations are returned (err1: |u' - u|^2, err2: |u'' - u'|^2 over the owned pixels).
+template <int PITCH>
+__device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int ucur, int pcur, int slot, int strip,
+                                          int lane, unsigned char* ring, double& err1, double& err2) {
+    using L = Lay<PITCH>;
+    constexpr int PB = (int)L::PB, ROWB = (int)L::ROWB;
+    const LevelGeom& g = P.lv[level];
+    const int W = g.W, H = g.H;
+    const InnerConst K = {P.l_t, P.theta, P.taut, P.negzero};
+
+    const int x0 = (strip % g.in2_sx) * kIW2;
+    const int y0 = (strip / g.in2_sx) * kIR2, y1 = min(y0 + kIR2, H);
+    const int c = x0 - 1 + lane;                              // this lane's column (-1 or >= W: dead halo lane)
+    const bool owner = lane >= 1 && lane <= kIW2 && c < W;    // lane owns the outputs of its column
+    const unsigned right_mask = (c + 1 < W) ? 0xffffffffu : 0u;   // forward x-difference exists
+    const unsigned not_col0 = (c > 0) ? 0xffffffffu : 0u;         // a left neighbour exists
+    const bool strip_at_x0 = (x0 == 0);                       // warp-uniform
+    const bool first_col = (c == 0);
+    const int rs = max(y0 - 2, 0);                            // first staged row (only its py is used when y0 >= 2)
+    const int ra = max(y0 - 1, 0);                            // first row of stage A
+    const int re = min(y1 + 1, H - 1);                        // last staged row / last row of stage A
+    const int qb = min(y1, H - 1);                            // last row of stages B and C
+
+    const char* sbase = reinterpret_cast<const char*>(slot_base(P, slot));
+    // staged columns [x0 - 2, x0 + 32), 16-byte aligned (x0 is even); the strips at x0 = 0 stage [0, 34) instead
+    // and read two columns further left in the segment (their lane 0, column -1, is a dead halo lane)
+    const int shift = strip_at_x0 ? 2 : 0;
+    const char* seg = sbase + ((size_t)rs * (size_t)ROWB + (size_t)(x0 - 2 + shift + kXMargin) * 8u);
+    const char* cu = seg + ucur * PB + lane * 16;                    // copy sources, this lane's 16 bytes (lane < 17)
+    const char* cc = seg + (int)PL_CA * PB + lane * 16;              // CA; CB at + PB
+    const char* cq = seg + ((int)PL_PX + pcur) * PB + lane * 16;     // PX[pcur]; PY[pcur] at + 2 PB
+    // stores: this lane's column in the partner planes; wu1 -> row r-1 (u''), wq2 -> row r-2 (p''), r = ra at first
+    char* wu1 = const_cast<char*>(sbase) + ((ptrdiff_t)(ra - 1) * ROWB + (ucur ^ 1) * PB + (c + kXMargin) * 8);
+    char* wq2 = const_cast<char*>(sbase) + ((ptrdiff_t)(ra - 2) * ROWB + ((int)PL_PX + (pcur ^ 1)) * PB + (c + kXMargin) * 8);
+    const uint32_t ring_cp = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+    const unsigned char* ring_rd = ring + (lane + 1 - shift) * 8;    // this lane's column inside a staged segment
+
+    const int n_rows = re - rs + 1;
+    int issued = 0;
+    auto issue_row = [&](int stage) {            // stage and issued are warp-uniform
+        if (issued < n_rows && lane < 17) {
+            const uint32_t d = ring_cp + stage * kStageB;
+            cp_async16(d, cu);
+            cp_async16(d + kSegB, cc);
+            cp_async16(d + 2 * kSegB, cc + PB);
+            cp_async16(d + 3 * kSegB, cq);
+            cp_async16(d + 4 * kSegB, cq + 2 * PB);
+        }
+        cp_async_commit();                       // an empty group keeps the group count per row constant
+        ++issued; cu += ROWB; cc += ROWB; cq += ROWB;
+    };
+    auto rd = [&](int stage, int plane, int off) {
+        return *reinterpret_cast<const float2*>(ring_rd + stage * kStageB + plane * kSegB + off);
+    };
+    auto diff_x = [&](float2 v) {                // forward x-difference (zero in the last image column)
+        const float2 d = sub2(make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1)), v);
+        return make_float2(and_mask(d.x, right_mask), and_mask(d.y, right_mask));
+    };
+    auto left_of = [&](float2 v) {               // the left neighbour's value (zero at the image border)
+        return make_float2(and_mask(__shfl_up_sync(0xffffffffu, v.x, 1), not_col0),
+                           and_mask(__shfl_up_sync(0xffffffffu, v.y, 1), not_col0));
+    };
+    auto st = [](char* p, int off, float2 v) { *reinterpret_cast<float2*>(p + off) = v; };
+    auto sq_norm = [](float2 a, float2 b) { const float2 d = sub2(a, b); const float2 q = mul2(d, d); return (double)(q.x + q.y); };
+
+#pragma unroll
+    for (int k = 0; k < kRing2; ++k) issue_row(k);
+
+    double e1 = 0.0, e2 = 0.0;
+    float2 u1p = make_float2(0.f, 0.f);                       // u'  of row r-1
+    float2 p1x = make_float2(0.f, 0.f), p1y = p1x;            // p'  of row r-2 (when a step starts)
+    float2 u2p = make_float2(0.f, 0.f);                       // u'' of row r-2 (when a step starts)
+    const float2 zero2 = make_float2(0.f, 0.f);
+
+    for (int r = ra; r <= y1 + 1; ++r) {
+        const int i = r - rs;                                  // staged row index of r
+        const int sc = i % kRing2, sp = (i + kRing2 - 1) % kRing2;   // ring stages of rows r and r-1
+        const bool has_a = r <= re;                            // row r exists (warp-uniform)
+        float2 u1 = zero2;
+        if (has_a) {
+            cp_async_wait<kRing2 - 2>();
+            __syncwarp();
+            InnerRow row;
+            row.u = rd(sc, 0, 0); row.ca = rd(sc, 1, 0); row.cb = rd(sc, 2, 0);
+            row.px = rd(sc, 3, 0); row.py = rd(sc, 4, 0);
+            const float2 l = rd(sc, 3, -8);
+            row.pxl = make_float2(and_mask(l.x, not_col0), and_mask(l.y, not_col0));
+            const float2 pyu = r >= 1 ? rd(sp, 4, 0) : zero2;
+            VStep v = estimate_v_fast(row, K);
+            if (v.bad) v.d = estimate_v_exact(row, v);
+            u1 = add2(add2(row.u, v.d), theta_div_px(row, row.pxl, pyu, strip_at_x0, first_col && r > 0, K));
+            if (owner && r >= y0 && r < y1) e1 += sq_norm(u1, row.u);
+        }
+        const int q = r - 1;
+        float2 n1x = zero2, n1y = zero2, u2 = zero2;          // p' and u'' of row q
+        if (q >= ra && q <= qb) {
+            // B(q): forwardGradient(u') + estimateDualVariables, first iteration
+            const float2 ux = diff_x(u1p);
+            const float2 uy = has_a ? sub2(u1, u1p) : zero2;
+            const float2 px0 = rd(sp, 3, 0), py0 = rd(sp, 4, 0);
+            if (!dual_update_fast(ux, uy, px0, py0, K, n1x, n1y)) dual_update_exact(ux, uy, px0, py0, K, n1x, n1y);
+            if (q >= y0) {
+                // C(q): estimateV + divergence(p') + estimateU, second iteration
+                InnerRow row;
+                row.u = u1p; row.ca = rd(sp, 1, 0); row.cb = rd(sp, 2, 0); row.px = n1x; row.py = n1y;
+                row.pxl = left_of(n1x);
+                const float2 pyu = q >= 1 ? p1y : zero2;
+                VStep v = estimate_v_fast(row, K);
+                if (v.bad) v.d = estimate_v_exact(row, v);
+                u2 = add2(add2(u1p, v.d), theta_div_px(row, row.pxl, pyu, strip_at_x0, first_col && q > 0, K));
+                if (owner && q < y1) { st(wu1, 0, u2); e2 += sq_norm(u2, u1p); }
+            }
+        }
+        const int q2 = r - 2;
+        if (q2 >= y0 && q2 < y1) {
+            // D(q2): forwardGradient(u'') + estimateDualVariables, second iteration
+            const float2 ux = diff_x(u2p);
+            const float2 uy = (q2 + 1 <= H - 1) ? sub2(u2, u2p) : zero2;
+            float2 pxn, pyn;
+            if (!dual_update_fast(ux, uy, p1x, p1y, K, pxn, pyn)) dual_update_exact(ux, uy, p1x, p1y, K, pxn, pyn);
+            if (owner) { st(wq2, 0, pxn); st(wq2, 2 * PB, pyn); }
+        }
+        u1p = u1; p1x = n1x; p1y = n1y; u2p = u2;
+        wu1 += ROWB; wq2 += ROWB;
+        __syncwarp();                                          // every lane has read row r-1: refill its stage
+        if (i >= 1) issue_row(sp);
+    }
+    cp_async_wait<0>();
+    __syncwarp();                                              // the ring may be refilled by this warp's next strip
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        e1 += __shfl_down_sync(0xffffffffu, e1, o);
+        e2 += __shfl_down_sync(0xffffffffu, e2, o);
+    }
+    err1 = e1; err2 = e2;
+}
+
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     const unsigned short lo = __half_as_ushort(__float2half_rn(a));
     const unsigned short hi = __half_as_ushort(__float2half_rn(b));
@@ -627,6 +818,7 @@ __global__ void __launch_bounds__(kThreads, TEEFLOW_MIN_CTAS)
 tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     __shared__ int s_prefix[kMaxSlots + 1];
     __shared__ float4 s_cubic[32];
+    extern __shared__ __align__(16) unsigned char s_ring[];   // [kWarpsPerCta][kRingB] when two-iteration passes are on
 
     // this launch serves the slot group [slot0, slot0 + S): groups run on separate streams so that the tail and
     // the launch gap of one group's step are filled by the other group's strips
@@ -685,6 +877,7 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
             case PH_WARP: op_warp<PITCH>(P, level, ucur, pair, slot, strip, lane, s_cubic); break;
             case PH_MEDIAN: op_median<PITCH>(P, level, ucur, slot, strip, lane); break;
             case PH_INNER: err = op_inner<PITCH>(P, level, ucur, pcur, slot, strip, lane); break;
+            case PH_INNER2: op_inner2<PITCH>(P, level, ucur, pcur, slot, strip, lane, s_ring + (tid >> 5) * kRingB, err, aux); break;
             case PH_WASE: op_wase<PITCH>(P, ucur, slot, strip, lane, err, aux); break;
             case PH_FINAL: op_final<PITCH>(P, ucur, pair, sp->bg, slot, strip, lane); break;
             default: break;
@@ -693,7 +886,7 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
         int last = 0;
         if (lane == 0) {
             if (phase == PH_INNER) P.partial[(size_t)slot * P.max_tiles + strip] = err;
-            if (phase == PH_WASE) {
+            if (phase == PH_WASE || phase == PH_INNER2) {
                 P.partial[(size_t)slot * P.max_tiles + 2 * strip] = err;
                 P.partial[(size_t)slot * P.max_tiles + 2 * strip + 1] = aux;
             }
@@ -711,7 +904,7 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
                 for (int t = lane; t < n_items; t += 32) e += __ldcg(part + t);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-            } else if (phase == PH_WASE) {
+            } else if (phase == PH_WASE || phase == PH_INNER2) {
                 const double* part = P.partial + (size_t)slot * P.max_tiles;
                 for (int t = lane; t < n_items; t += 32) { e += __ldcg(part + 2 * t); e2 += __ldcg(part + 2 * t + 1); }
 #pragma unroll
@@ -735,7 +928,7 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
                     __threadfence();
                     atomicAdd(P.pairs_done, 1);
                 } else {
-                    advance_slot(P, n, e);
+                    advance_slot(P, n, e, e2);
                 }
                 nxt[lo] = n;
                 P.arrive[slot] = 0u;

@@ -245,6 +245,27 @@ def test_fast_hypot_matches_double_precision_hypot(engine, mode):
         assert rej.value < n // 1000, rej.value
 
 
+@pytest.mark.parametrize("spec", [1.01, 2.0, 8.0])
+def test_two_iteration_passes_change_nothing(oracle, spec):
+    """temporal blocking of the inner loop (two iterations per pass, speculative exit test, spec_factor > 0) yields the
+    same flow bits and the same per-level iteration counts as the oracle -- whatever the speculation threshold,
+    including discarded passes"""
+    from tee_optical_flow_b200.synth import make_clip
+    fr = make_clip(seed=11, n_frames=4, H=150, W=203, peak_disp=6.0, period=8.0)
+    with _fresh() as eng:
+        eng._set("spec_factor", spec)
+        flow, _ = eng.calc_clip(fr, duplicate_last=False)
+        counters, info = eng.last_counters()
+    assert info["double_steps"] > 0
+    if spec < 1.5:
+        assert info["double_steps_discarded"] > 0      # the low threshold must exercise the discard path
+    om = oracle.OracleDualTVL1(err_mode=1)
+    for i in range(3):
+        ref = om.calc(fr[i], fr[i + 1])
+        assert np.all(flow[i] == ref), f"pair {i}: mean EPE {_epe(flow[i], ref).mean():.3e}"
+        assert np.array_equal(counters[i], om.last_counters[:counters.shape[1]])
+
+
 def test_batch_of_clips_equals_per_clip():
     """BASELINE config 4 (one rank's share): several clips through one scheduler run, slots refilled across clips"""
     import torch
