@@ -62,7 +62,9 @@ struct teeflow_engine {
     unsigned* arrive = nullptr;
     double* partial = nullptr;
     int* ctl = nullptr;        // [0] next_pair, [1] pairs_done
-    int* pair_lists = nullptr; // [4][cap_pairs]
+    int* pair_lists = nullptr; // [5][cap_pairs]: pair_a, pair_b, out_index, dup_index, done_order
+    int* h_order = nullptr;    // pinned [2][cap_pairs]: snapshots of done_order
+    cudaStream_t copy_stream = nullptr;   // early device-to-host copies of finished flows (host-buffer entry points)
     int* counters = nullptr;   // [cap_pairs][kMaxLevels][3]
     float* bg = nullptr;       // [cap_pairs] WASE background scalars
     const float* wase_w = nullptr;  // caller-owned [H][W][2] weight map (nullptr: no background compensation)
@@ -195,6 +197,7 @@ int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
     CU_TRY(h, cudaEventCreate(&h->ev_t1));
     CU_TRY(h, cudaEventCreate(&h->ev_tp));
     CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int g = 0; g < kMaxGroups - 1; ++g) {
         CU_TRY(h, cudaStreamCreateWithFlags(&h->group_stream[g], cudaStreamNonBlocking));
         for (int w = 0; w < 2; ++w) CU_TRY(h, cudaEventCreateWithFlags(&h->ev_group[w][g], cudaEventDisableTiming));
@@ -218,6 +221,8 @@ int teeflow_destroy(teeflow_handle h) {
     cudaFree(h->ccl_sr); cudaFree(h->ccl_sc); cudaFree(h->ccl_best);
     cudaFree(h->stage_in); cudaFree(h->stage_f32); cudaFree(h->stage_f16);
     cudaFreeHost(h->h_done);
+    if (h->h_order) cudaFreeHost(h->h_order);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
     if (h->ev_t1) cudaEventDestroy(h->ev_t1);
@@ -444,7 +449,10 @@ static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_strid
     }
     if (n_pairs > h->cap_pairs) {
         h->cap_pairs = 0;
-        CU_TRY(h, regrow(h->pair_lists, 4 * n_pairs));
+        CU_TRY(h, regrow(h->pair_lists, 5 * n_pairs));
+        if (h->h_order) cudaFreeHost(h->h_order);
+        h->h_order = nullptr;
+        CU_TRY(h, cudaMallocHost(&h->h_order, sizeof(int) * 2 * n_pairs));
         CU_TRY(h, regrow(h->counters, n_pairs * kMaxLevels * 3));
         CU_TRY(h, regrow(h->bg, n_pairs));
         h->cap_pairs = n_pairs;
@@ -452,10 +460,12 @@ static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_strid
     return TEEFLOW_OK;
 }
 
+// host_f32 / host_f16 (optional): host mirrors of the output buffers; the flow of a finished pair is copied out while
+// the other pairs are still being solved (a frame pair is an independent unit, its result is final once written)
 static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n_frames, int H, int W,
                      int64_t frame_stride, const int32_t* pair_a, const int32_t* pair_b, const int32_t* out_index,
                      const int32_t* dup_index, int n_pairs, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, float* host_f32 = nullptr, void* host_f16 = nullptr) {
     if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
     if (!frames_dev || !pair_a || !pair_b || !out_index || !dup_index)
         return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL frames or pair list");
@@ -525,6 +535,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     P.spec_stats = h->ctl + 2 + 2 * kMaxGroups;
     P.pair_a = h->pair_lists; P.pair_b = h->pair_lists + h->cap_pairs;
     P.out_index = h->pair_lists + 2 * h->cap_pairs; P.dup_index = h->pair_lists + 3 * h->cap_pairs;
+    P.done_order = h->pair_lists + 4 * h->cap_pairs;
     P.counters_out = h->counters;
     P.wase_w = h->wase_w;
     P.bg_out = h->bg;
@@ -533,6 +544,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
 
     CU_TRY(h, cudaEventRecord(h->ev_t0, stream));
     CU_TRY(h, cudaMemsetAsync(h->bg, 0, sizeof(float) * n_pairs, stream));
+    CU_TRY(h, cudaMemsetAsync(P.done_order, 0xFF, sizeof(int) * n_pairs, stream));
     // pair lists (small) -- pageable host memory: the copies are staged by the runtime before the call returns
     CU_TRY(h, cudaMemcpyAsync((void*)P.pair_a, pair_a, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream));
     CU_TRY(h, cudaMemcpyAsync((void*)P.pair_b, pair_b, sizeof(int) * n_pairs, cudaMemcpyHostToDevice, stream));
@@ -619,6 +631,24 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     bool done = false;
     volatile int* hd = h->h_done;
     hd[0] = hd[1] = 0;
+    // early copy-out of finished pairs (host-buffer entry points)
+    const bool copy_out = host_f32 || host_f16;
+    const size_t npx_out = (size_t)H * W;
+    int n_copied = 0;
+    auto copy_pair = [&](int pair) -> cudaError_t {
+        const int idx[2] = {out_index[pair], dup_index[pair]};
+        for (int k = 0; k < 2; ++k) {
+            if (idx[k] < 0) continue;
+            cudaError_t e = cudaSuccess;
+            if (host_f32) e = cudaMemcpyAsync(host_f32 + (size_t)idx[k] * npx_out * 2, flow_f32_dev + (size_t)idx[k] * npx_out * 2,
+                                              npx_out * 8, cudaMemcpyDeviceToHost, h->copy_stream);
+            if (e == cudaSuccess && host_f16)
+                e = cudaMemcpyAsync((char*)host_f16 + (size_t)idx[k] * npx_out * 4, (char*)flow_f16_dev + (size_t)idx[k] * npx_out * 4,
+                                    npx_out * 4, cudaMemcpyDeviceToHost, h->copy_stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
     while (!done) {
         if (step > max_steps) return fail(h, TEEFLOW_ERR_STATE, "scheduler exceeded %lld steps", max_steps);
         for (int k = 0; k < chunk; ++k, ++step)
@@ -636,12 +666,21 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
             CU_TRY(h, cudaStreamWaitEvent(stream, h->ev_group[which][g - 1], 0));
         }
         CU_TRY(h, cudaMemcpyAsync((void*)(hd + which), h->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        if (copy_out)
+            CU_TRY(h, cudaMemcpyAsync(h->h_order + (size_t)which * h->cap_pairs, P.done_order, sizeof(int) * n_pairs,
+                                      cudaMemcpyDeviceToHost, stream));
         CU_TRY(h, cudaEventRecord(h->ev[which], stream));
         for (int g = 1; g < G; ++g) CU_TRY(h, cudaStreamWaitEvent(gs[g], h->ev[which], 0));
         if (++n_chunks >= 2) {
             const int prev = which ^ 1;
             CU_TRY(h, cudaEventSynchronize(h->ev[prev]));
             if (hd[prev] >= n_pairs) done = true;
+            if (copy_out) {
+                // every launch up to that chunk has completed: the flows of the pairs it lists are final
+                const int* order = h->h_order + (size_t)prev * h->cap_pairs;
+                while (n_copied < n_pairs && n_copied < hd[prev] && order[n_copied] >= 0)
+                    CU_TRY(h, copy_pair(order[n_copied++]));
+            }
         }
     }
     CU_TRY(h, cudaEventRecord(h->ev_t1, stream));
@@ -652,6 +691,16 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         int d = 0;
         CU_TRY(h, cudaMemcpy(&d, h->ctl + 1, sizeof(int), cudaMemcpyDeviceToHost));
         if (d < n_pairs) return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", d, n_pairs);
+    }
+    if (copy_out) {
+        // the rest: everything is complete now
+        CU_TRY(h, cudaMemcpy(h->h_order, P.done_order, sizeof(int) * n_pairs, cudaMemcpyDeviceToHost));
+        for (; n_copied < n_pairs; ++n_copied) {
+            const int pair = h->h_order[n_copied];
+            if (pair < 0 || pair >= n_pairs) return fail(h, TEEFLOW_ERR_STATE, "completion list is corrupt at %d", n_copied);
+            CU_TRY(h, copy_pair(pair));
+        }
+        CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
     }
     step *= G;
     for (int i = 0; i < h->n_launches_timed; ++i)
@@ -721,11 +770,15 @@ int teeflow_calc_clip_host(teeflow_handle h, const void* frames_host, int dtype,
     if (flow_f16_host && (rc = ensure_stage(h, h->stage_f16, h->stage_f16_bytes, n_out * npx * 4))) return rc;
     cudaStream_t st = h->own_stream;
     CU_TRY(h, cudaMemcpyAsync(h->stage_in, frames_host, npx * esz * n_frames, cudaMemcpyHostToDevice, st));
-    rc = teeflow_calc_clip(h, h->stage_in, dtype, n_frames, H, W, (int64_t)npx, flow_f32_host ? (float*)h->stage_f32 : nullptr,
-                           flow_f16_host ? h->stage_f16 : nullptr, out_scale, duplicate_last, (void*)st);
+    const int n_pairs = n_frames - 1;
+    std::vector<int32_t> a(n_pairs), b(n_pairs), o(n_pairs), d(n_pairs, -1);
+    for (int i = 0; i < n_pairs; ++i) { a[i] = i; b[i] = i + 1; o[i] = i; }
+    if (duplicate_last) d[n_pairs - 1] = n_pairs;
+    // finished pairs are copied to the host buffers while the others are still being solved
+    rc = run_pairs(h, h->stage_in, dtype, n_frames, H, W, (int64_t)npx, a.data(), b.data(), o.data(), d.data(), n_pairs,
+                   flow_f32_host ? (float*)h->stage_f32 : nullptr, flow_f16_host ? h->stage_f16 : nullptr, out_scale, st,
+                   flow_f32_host, flow_f16_host);
     if (rc) return rc;
-    if (flow_f32_host) CU_TRY(h, cudaMemcpyAsync(flow_f32_host, h->stage_f32, n_out * npx * 8, cudaMemcpyDeviceToHost, st));
-    if (flow_f16_host) CU_TRY(h, cudaMemcpyAsync(flow_f16_host, h->stage_f16, n_out * npx * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(h, cudaStreamSynchronize(st));
     return TEEFLOW_OK;
 }

@@ -920,13 +920,14 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
                     P.bg_out[n.pair] = n.bg;
                     n.phase = PH_FINAL;
                 } else if (n.phase == PH_FINAL) {
+                    const int finished = n.pair;
                     int* co = P.counters_out + (size_t)n.pair * kMaxLevels * 3;
                     for (int l = 0; l < kMaxLevels; ++l) { co[l * 3] = n.cnt[l][0]; co[l * 3 + 1] = n.cnt[l][1]; co[l * 3 + 2] = n.cnt[l][2]; }
                     const int next = atomicAdd(P.next_pair, 1);
                     if (next < P.n_pairs) start_pair(P, n, next);
                     else { n.pair = -1; n.phase = PH_IDLE; }
                     __threadfence();
-                    atomicAdd(P.pairs_done, 1);
+                    P.done_order[atomicAdd(P.pairs_done, 1)] = finished;   // the host copies finished flows out early
                 } else {
                     advance_slot(P, n, e, e2);
                 }
