@@ -241,7 +241,7 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
         const float i0 = i0_n;
         if (y + 1 < y1) { u_n = __ldg(row + oU + L::ROW); i0_n = __ldg(I0 + q + (unsigned)g.W); }
         const float mx = (float)x + u.x, my = (float)y + u.y;
-        const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic);
+        const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic, P.negzero);
         const float Ix2 = w.y * w.y, Iy2 = w.z * w.z;
         row[PL_CA * PITCH] = make_float2(w.y, w.z);
         row[PL_CB * PITCH] = make_float2(Ix2 + Iy2, (w.x - w.y * u.x - w.z * u.y - i0));
