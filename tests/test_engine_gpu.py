@@ -266,6 +266,23 @@ def test_two_iteration_passes_change_nothing(oracle, spec):
         assert np.array_equal(counters[i], om.last_counters[:counters.shape[1]])
 
 
+def test_two_iteration_passes_full_size_equal_single_iteration_passes():
+    """600x800: the flow bits and the executed iteration counts do not depend on the temporal-blocking option"""
+    import torch
+    from tee_optical_flow_b200.synth import make_clip
+    fr = torch.from_numpy(make_clip(seed=5, n_frames=7, H=600, W=800)).cuda()
+    out = []
+    for spec in (0.0, 1.5):
+        with _fresh() as eng:
+            eng._set("spec_factor", spec)
+            f32, _ = eng.calc_clip(fr)
+            counters, info = eng.last_counters()
+            out.append((f32.cpu().numpy(), counters, info))
+    assert out[0][2]["double_steps"] == 0 and out[1][2]["double_steps"] > 0
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    assert np.array_equal(out[0][1], out[1][1])
+
+
 def test_batch_of_clips_equals_per_clip():
     """BASELINE config 4 (one rank's share): several clips through one scheduler run, slots refilled across clips"""
     import torch
