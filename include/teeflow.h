@@ -147,6 +147,14 @@ TEEFLOW_API int teeflow_level_sizes(teeflow_handle h, int H, int W, int32_t* Hs,
 TEEFLOW_API int teeflow_prepare_frames(teeflow_handle h, const uint8_t* rgb_dev, int n_frames, int H, int W,
                                        uint8_t* gray_dev, void* stream);
 
+/* ---- saliency input stage: the `no_saliency=False` branch, cv2.saliency.StaticSaliencyFineGrained_create()
+ * .computeSaliency(frame) per frame (calculate_optical_flow.py:560, :586).  rgb_dev: (n_frames,H,W,3) uint8;
+ * saliency_dev: (n_frames,H,W) float32 in [0,1] (what computeSaliency returns and the solver takes as its image),
+ * intensity_dev: the uint8 conspicuity map before the 1/255 scaling; either may be NULL.  Device pointers,
+ * asynchronous on `stream`.  Parity status: csrc/saliency_kernels.cuh. */
+TEEFLOW_API int teeflow_saliency_fine_grained(teeflow_handle h, const uint8_t* rgb_dev, int n_frames, int H, int W,
+                                              float* saliency_dev, uint8_t* intensity_dev, void* stream);
+
 /* ---- mask post-processing and AV centroid (connected components on the GPU)
  * teeflow_clean_masks: the per-label pipeline of clean_mask (calculate_optical_flow.py:113-182) on a class map
  * (n_frames,H,W) uint8 (SAM argmax): (class == class_id) -> moving_avg_mask(window, threshold) over frames (:91-111)

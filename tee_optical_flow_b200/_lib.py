@@ -82,6 +82,8 @@ SIGNATURES = {
     "teeflow_analysis_histogram": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int64),
                                              C.c_void_p]),
     "teeflow_selftest_division": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_int64)]),
+    "teeflow_saliency_fine_grained": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
     "teeflow_time_launches": (C.c_int, [C.c_void_p, C.c_int]),
     "teeflow_get_launch_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "teeflow_selftest_hypot": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.POINTER(C.c_int64),

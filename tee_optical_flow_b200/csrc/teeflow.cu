@@ -17,6 +17,7 @@
 #include "../../include/teeflow.h"
 #include "tvl1_kernels.cuh"
 #include "finalize_kernels.cuh"
+#include "saliency_kernels.cuh"
 
 using namespace teeflow;
 
@@ -78,6 +79,12 @@ struct teeflow_engine {
     long long* an_ranks = nullptr;
     unsigned long long* an_keys = nullptr;
     unsigned long long* prep_mm = nullptr; size_t prep_cap = 0;
+    // saliency scratch (teeflow_saliency_fine_grained), sized for kSalChunk frames
+    size_t sal_cap = 0;
+    uint8_t *sal_g0 = nullptr, *sal_g1 = nullptr, *sal_on = nullptr, *sal_off = nullptr;
+    float *sal_prefix = nullptr, *sal_integ = nullptr;
+    uint16_t *sal_son = nullptr, *sal_soff = nullptr;
+    SalMax* sal_max = nullptr;
     // connected-component scratch (teeflow_clean_masks / teeflow_av_centroids), sized for kCclChunk frames
     size_t ccl_cap = 0;
     int *ccl_L = nullptr, *ccl_area = nullptr, *ccl_touch = nullptr, *ccl_ncomp = nullptr;
@@ -217,6 +224,8 @@ int teeflow_destroy(teeflow_handle h) {
     cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
     cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
     cudaFree(h->an_edges); cudaFree(h->an_freq); cudaFree(h->prep_mm);
+    cudaFree(h->sal_g0); cudaFree(h->sal_g1); cudaFree(h->sal_on); cudaFree(h->sal_off); cudaFree(h->sal_prefix);
+    cudaFree(h->sal_integ); cudaFree(h->sal_son); cudaFree(h->sal_soff); cudaFree(h->sal_max);
     cudaFree(h->ccl_L); cudaFree(h->ccl_area); cudaFree(h->ccl_touch); cudaFree(h->ccl_ncomp);
     cudaFree(h->ccl_sr); cudaFree(h->ccl_sc); cudaFree(h->ccl_best);
     cudaFree(h->stage_in); cudaFree(h->stage_f32); cudaFree(h->stage_f16);
@@ -874,6 +883,48 @@ int teeflow_prepare_frames(teeflow_handle h, const uint8_t* rgb_dev, int n_frame
     prep_quantize_kernel<<<grid, 256, 0, stream>>>(rgb_dev, npx, h->prep_mm, gray_dev);
     CU_TRY(h, cudaGetLastError());
     CU_TRY(h, cudaStreamSynchronize(stream));     // `init` is a host temporary
+    return TEEFLOW_OK;
+}
+
+// ---- saliency input stage: cv2.saliency.StaticSaliencyFineGrained.computeSaliency per frame
+// (calculate_optical_flow.py:560, :586); kernels and the parity status in saliency_kernels.cuh
+static const int kSalChunk = 16;
+
+int teeflow_saliency_fine_grained(teeflow_handle h, const uint8_t* rgb_dev, int n_frames, int H, int W,
+                                  float* saliency_dev, uint8_t* intensity_dev, void* stream_v) {
+    if (!h || !rgb_dev || (!saliency_dev && !intensity_dev) || n_frames < 1) return fail(h, TEEFLOW_ERR_BAD_ARG, "bad argument");
+    if (H < 3 || W < 3 || (int64_t)(H + 1) * (W + 1) > (1 << 28)) return fail(h, TEEFLOW_ERR_BAD_SHAPE, "bad frame shape %dx%d", H, W);
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t npx = (size_t)H * W, nint = (size_t)(H + 1) * (W + 1);
+    if (nint > h->sal_cap) {
+        h->sal_cap = 0;
+        CU_TRY(h, regrow(h->sal_g0, npx * kSalChunk)); CU_TRY(h, regrow(h->sal_g1, npx * kSalChunk));
+        CU_TRY(h, regrow(h->sal_on, npx * kSalChunk)); CU_TRY(h, regrow(h->sal_off, npx * kSalChunk));
+        CU_TRY(h, regrow(h->sal_prefix, npx * kSalChunk)); CU_TRY(h, regrow(h->sal_integ, nint * kSalChunk));
+        CU_TRY(h, regrow(h->sal_son, npx * kSalChunk)); CU_TRY(h, regrow(h->sal_soff, npx * kSalChunk));
+        if (!h->sal_max) CU_TRY(h, regrow(h->sal_max, (size_t)kSalChunk));
+        h->sal_cap = nint;
+    }
+    const dim3 blk(32, 8);
+    for (int f0 = 0; f0 < n_frames; f0 += kSalChunk) {
+        const int nf = std::min(kSalChunk, n_frames - f0);
+        const int tot = (int)std::min<size_t>(npx * nf, (size_t)INT_MAX);
+        const dim3 g2((W + 31) / 32, (H + 7) / 8, nf);
+        const dim3 g1(std::max(1, std::min((int)((npx + 1023) / 1024), 256)), nf);
+        CU_TRY(h, cudaMemsetAsync(h->sal_max, 0, sizeof(SalMax) * kSalChunk, stream));
+        sal_gray_kernel<<<std::max(1, std::min((tot + 255) / 256, 4096)), 256, 0, stream>>>(rgb_dev + (size_t)f0 * npx * 3, tot, h->sal_g0);
+        sal_blur5_kernel<<<g2, blk, 0, stream>>>(h->sal_g0, h->sal_g1, nf, H, W);
+        sal_blur5_kernel<<<g2, blk, 0, stream>>>(h->sal_g1, h->sal_g0, nf, H, W);
+        sal_rowprefix_kernel<<<(nf * H + 7) / 8, 256, 0, stream>>>(h->sal_g0, h->sal_prefix, nf * H, W);
+        sal_integral_kernel<<<dim3((W + 1 + 127) / 128, nf), 128, 0, stream>>>(h->sal_prefix, h->sal_integ, nf, H, W);
+        sal_scales_kernel<<<g2, blk, 0, stream>>>(h->sal_g0, h->sal_integ, nf, H, W, h->sal_son, h->sal_soff, h->sal_max);
+        sal_mix_kernel<<<g1, 256, 0, stream>>>(h->sal_son, h->sal_soff, nf, (int)npx, h->sal_on, h->sal_off, h->sal_max);
+        sal_final_kernel<<<g1, 256, 0, stream>>>(h->sal_on, h->sal_off, nf, (int)npx, h->sal_max,
+                                                 saliency_dev ? saliency_dev + (size_t)f0 * npx : nullptr,
+                                                 intensity_dev ? intensity_dev + (size_t)f0 * npx : nullptr);
+        CU_TRY(h, cudaGetLastError());
+    }
     return TEEFLOW_OK;
 }
 

@@ -267,6 +267,25 @@ class TVL1Engine:
         self._check(self._lib.teeflow_prepare_frames(self._h, t.data_ptr(), N, H, W, out.data_ptr(), C.c_void_p(stream)))
         return out.cpu().numpy() if is_np else out
 
+    def compute_saliency(self, rgb, return_u8: bool = False):
+        """cv2.saliency.StaticSaliencyFineGrained.computeSaliency per frame (calculate_optical_flow.py:560, :586)
+        on the GPU: (N,H,W,3) uint8 -> (N,H,W) float32 in [0,1] (or the uint8 map with return_u8).  numpy -> numpy,
+        CUDA torch tensor -> CUDA torch tensor.  Parity status: csrc/saliency_kernels.cuh."""
+        import torch
+        is_np = isinstance(rgb, np.ndarray)
+        t = torch.from_numpy(np.ascontiguousarray(rgb)) if is_np else rgb
+        if t.dtype != torch.uint8 or t.dim() != 4 or t.shape[-1] != 3:
+            raise OpticalFlowCalculationError("rgb frames must be (N, H, W, 3) uint8")
+        t = t.to(torch.device("cuda", self.device)).contiguous()
+        N, H, W, _ = t.shape
+        out = torch.empty((N, H, W), dtype=torch.uint8 if return_u8 else torch.float32, device=t.device)
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        self._check(self._lib.teeflow_saliency_fine_grained(
+            self._h, t.data_ptr(), N, H, W, None if return_u8 else out.data_ptr(), out.data_ptr() if return_u8 else None,
+            C.c_void_p(stream)))
+        torch.cuda.current_stream(t.device).synchronize()
+        return out.cpu().numpy() if is_np else out
+
     # ------------------------------------------------------------------ WASE background compensation
     def set_wase_masks(self, bkgd_mask) -> None:
         """bkgd_comp='WASE' (calculate_optical_flow.py:649-652): `bkgd_mask` is mask_dict['bkgd'], (N, H, W, 2) bool

@@ -104,10 +104,9 @@ def process_frames(frames: np.ndarray, mask_dict: Optional[Dict[str, np.ndarray]
                                           else "OF_algo='deepflow' is outside this engine (TV-L1 path only)")
     if bkgd_comp not in ('WASE', 'none'):
         raise OpticalFlowCalculationError(f'bkgd_comp value must be [WASE, none], got {bkgd_comp}!')
-    if not no_saliency:
-        raise OpticalFlowCalculationError("saliency input (cv2.saliency) is a 'next' row (SURVEY.md §8f); "
-                                          "pass no_saliency=True")
     frames = np.asarray(frames)
+    if not no_saliency and not (frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[-1] == 3):
+        raise OpticalFlowCalculationError('no_saliency=False needs (N,H,W,3) uint8 frames (computeSaliency input, :586)')
     if frames.shape[0] < 2:
         raise OpticalFlowCalculationError('need at least two frames')
     mask_dict = mask_dict or {}
@@ -120,13 +119,16 @@ def process_frames(frames: np.ndarray, mask_dict: Optional[Dict[str, np.ndarray]
     if own:
         engine = TVL1Engine(**config.tvl1_params())
     try:
-        if frames_are_prepared:
+        if not no_saliency:
+            # saliency_obj.computeSaliency(frame) per frame (:586): float32 maps in [0,1] are the solver's images
+            gray_u8 = engine.compute_saliency(frames)
+        elif frames_are_prepared:
             gray_u8 = frames
         elif frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[-1] == 3:
             gray_u8 = engine.prepare_frames(frames)          # img2uint8(rgb2gray(.)) on the GPU (:588)
         else:
             gray_u8 = prepare_frames(frames)                 # unusual input dtypes: host formula
-        if gray_u8.dtype != np.uint8 or gray_u8.ndim != 3:
+        if gray_u8.ndim != 3 or gray_u8.dtype != (np.uint8 if no_saliency else np.float32):
             raise OpticalFlowCalculationError('prepared frames must be (N,H,W) uint8')
         engine.set_wase_masks(mask_dict['bkgd'] if bkgd_comp == 'WASE' else None)
         # pair loop (:584-597) + copy of the last flow (:599) + * conversion_factor (:600) + astype(float16) (:403)
