@@ -299,6 +299,16 @@ def main():
         barrier()
         analysis = {"ms_per_clip": 1e3 * (time.perf_counter() - a0) / reps, "frames": nfr,
                     "what": "teeflow_analyze_clip (mag p99, angle mode, radial/longitudinal p1/p99) + waveform gather"}
+        # saliency input stage of config 3 ("saliency on"): StaticSaliencyFineGrained per frame on the GPU
+        rgb = frames_dev.unsqueeze(-1).expand(-1, -1, -1, 3).contiguous()
+        eng.compute_saliency(rgb)
+        barrier()
+        s0 = time.perf_counter()
+        for _ in range(reps):
+            eng.compute_saliency(rgb)
+        barrier()
+        analysis["saliency_ms_per_clip"] = 1e3 * (time.perf_counter() - s0) / reps
+        analysis["saliency_what"] = "teeflow_saliency_fine_grained, 64 RGB frames 600x800 -> float32 maps"
     except Exception as e:  # informational only
         analysis = {"error": str(e)[:200]}
 
