@@ -907,9 +907,10 @@ int teeflow_saliency_fine_grained(teeflow_handle h, const uint8_t* rgb_dev, int 
         h->sal_cap = nint;
     }
     const dim3 blk(32, 8);
-    for (int f0 = 0; f0 < n_frames; f0 += kSalChunk) {
-        const int nf = std::min(kSalChunk, n_frames - f0);
-        const int tot = (int)std::min<size_t>(npx * nf, (size_t)INT_MAX);
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>(kSalChunk, (size_t)INT_MAX / npx));   // 32-bit pixel index per chunk
+    for (int f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = std::min(chunk, n_frames - f0);
+        const int tot = (int)(npx * nf);
         const dim3 g2((W + 31) / 32, (H + 7) / 8, nf);
         const dim3 g1(std::max(1, std::min((int)((npx + 1023) / 1024), 256)), nf);
         CU_TRY(h, cudaMemsetAsync(h->sal_max, 0, sizeof(SalMax) * kSalChunk, stream));
