@@ -9,6 +9,26 @@ from tee_optical_flow_b200.engine import TVL1Engine
 from tee_optical_flow_b200.synth import make_clip, make_masks
 
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
+if which in ("3", "both"):
+    # config 3: saliency on + TV-L1 on the saliency maps + masked radial / longitudinal decomposition of the stored flow
+    from tee_optical_flow_b200.sharding import WAVEFORM_COLUMNS
+    clip = make_clip(seed=0, n_frames=64, H=600, W=800)
+    rgb = torch.from_numpy(np.repeat(clip[..., None], 3, -1)).cuda()
+    rv = torch.from_numpy(make_masks(0, 64, 600, 800)["rv"]).cuda()
+    cent = np.tile(np.array([[0.77 * 600, 0.5 * 800]]), (62, 1))
+    eng = TVL1Engine(device=0)
+    for rep in range(2):
+        torch.cuda.synchronize(); t = time.time()
+        sal = eng.compute_saliency(rgb)
+        torch.cuda.synchronize(); t1 = time.time()
+        _, f16 = eng.calc_clip(sal, want_f32=False, want_f16=True)
+        torch.cuda.synchronize(); t2 = time.time()
+        res = eng.analyze_clip(f16, rv, cent, 62)
+        torch.cuda.synchronize(); t3 = time.time()
+    c, info = eng.last_counters()
+    print(f"config3: saliency {1e3*(t1-t):.1f} ms + TV-L1 on the saliency maps {1e3*(t2-t1):.1f} ms ({63/(t2-t1):.0f} pairs/s, "
+          f"{c[:, :, 0].sum() / 63:.0f} inner iterations/pair) + decomposition {1e3*(t3-t2):.1f} ms", flush=True)
+    eng.close()
 if which in ("4", "both"):
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 8
     clips = torch.from_numpy(np.stack([make_clip(seed=s, n_frames=64, H=600, W=800) for s in range(B)])).cuda()
