@@ -174,9 +174,10 @@ def phase_probe(frames_dev, device):
         t = eng.launch_times_ms()
         ms = t if ms is None else np.minimum(ms, t[:len(ms)])
     eng.close()
-    inner_ms = float(np.median(ms[3:9]))
-    out = {"what": "63 pairs x 600x800 px per launch, one pyramid level, lockstep launches (best of 3 runs)",
-           "px_per_launch": px}
+    inner_ms = float(ms[3])     # launch 3 is always a single iteration (the first of the loop)
+    out = {"what": "63 pairs x 600x800 px per launch, one pyramid level, lockstep launches (best of 3 runs); launches "
+                   "4.. are two-iteration passes when the temporal blocking is on",
+           "px_per_launch": px, "launch_ms": [round(float(x), 4) for x in ms]}
     for name, t, b in (("level_init", float(ms[0]), 24), ("warp", float(ms[1]), 32), ("median", float(ms[2]), 16),
                        ("inner", inner_ms, 64)):
         gbs = px * b / (t * 1e-3) / 1e9

@@ -36,6 +36,7 @@
  * -ffp-contract=off (no FMA contraction) -- see oracle/Makefile.
  */
 #include <float.h>
+#include <stdio.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -452,6 +453,9 @@ TF_EXPORT double oracle_inner_iteration(const float* I1wx, const float* I1wy, co
 }
 
 /* procOneScale; counters[0..2] += inner iterations, median passes, warps executed */
+static int g_trace = 0;
+TF_EXPORT void oracle_set_trace(int on) { g_trace = on; }
+
 static void proc_one_scale(const tvl1_oracle_params* P, const float* I0, const float* I1, float* u1, float* u2,
                            int H, int W, scratch_t* S, int* counters) {
     const size_t n = (size_t)H * W;
@@ -484,6 +488,9 @@ static void proc_one_scale(const tvl1_oracle_params* P, const float* I0, const f
                 forward_gradient(u2, H, W, S->u2x, S->u2y);
                 estimate_dual(S->u1x, S->u1y, S->u2x, S->u2y, S->p11, S->p12, S->p21, S->p22, taut, H, W);
                 counters[0]++;
+                /* diagnostics for the engine's speculation policy (tools/spec_policy.py): error / threshold */
+                if (g_trace) fprintf(stderr, "TRACE %dx%d warp %d outer %d inner %d err_over_eps %.6g\n", H, W, warpings,
+                                     n_outer, n_inner, (double)error / (double)scaledEpsilon);
             }
         }
     }

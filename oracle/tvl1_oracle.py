@@ -30,7 +30,7 @@ class _Params(C.Structure):
 
 def build(force: bool = False) -> Path:
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    srcs = [_HERE / "tvl1_oracle.c", _HERE / "downstream_oracle.c"]
+    srcs = [_HERE / "tvl1_oracle.c", _HERE / "Makefile"]
     if (not force and _LIB_PATH.exists()
             and all(_LIB_PATH.stat().st_mtime >= s.stat().st_mtime for s in srcs)):
         return _LIB_PATH

@@ -18,8 +18,9 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libteeflow.so"
 SOURCES = [CSRC / "teeflow.cu"]
-HEADERS = [CSRC / "tvl1_device.cuh", CSRC / "tvl1_kernels.cuh", CSRC / "finalize_kernels.cuh", CSRC / "median_networks.inc",
-           PKG.parent / "include" / "teeflow.h"]
+# every header the translation unit can include: a stale library after an edit would go unnoticed by the tests
+HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc")) + sorted(CSRC.glob("*.h")) + \
+    [PKG.parent / "include" / "teeflow.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -7,8 +7,8 @@ reference, and BASELINE config 5 (7 scales, 10 warps) can be expressed.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
-from typing import Optional
+from dataclasses import dataclass, field
+from typing import List, Optional
 
 
 @dataclass
@@ -51,3 +51,57 @@ class OpticalFlowCalculationConfig:
 def default_optical_flow_config() -> OpticalFlowCalculationConfig:
     """Create default optical flow calculation configuration (config.py:191)."""
     return OpticalFlowCalculationConfig()
+
+
+# ---- the downstream configs the waveform pipeline (waveforms.py) reads; field names and defaults of the reference
+@dataclass
+class CardiacCycleConfig:
+    """optical_flow/config.py:12-29.  Only smooth_fraction / pad_len act on the angle-based detector of this path;
+    the remaining fields belong to the ECG / arterial / area detectors (out of scope) and keep the schema intact."""
+    smooth_fraction: float = 0.2
+    pad_len: int = 20
+    sys_thres: float = 0.9
+    dia_thres: float = 0.5
+    rr_sys_ratio: float = 0.333
+    sys_extension: int = 2
+    t_peak_thres: float = 0.5
+    t_min_dist: int = 20
+    rr_search_range: List[float] = field(default_factory=lambda: [0.2, 0.75])
+    low_peak_thres: float = 0.9
+    low_min_dist: int = 50
+    high_peak_thres: float = 0.9
+    high_min_dist: int = 50
+    sys_upstroke_multiplier: int = 2
+    sys_upstroke_offset: int = 5
+
+
+@dataclass
+class PeakDetectionConfig:
+    """optical_flow/config.py:74-82."""
+    peak_thres: float = 0.2
+    min_dist: int = 5
+    pick_peak_by_subset: bool = True
+    show_all_peaks: bool = False
+    smooth_fraction: float = 0.3
+    pad_len: int = 20
+
+
+@dataclass
+class AnalysisConfig:
+    """optical_flow/config.py:85-95."""
+    percentile: int = 99
+    perc_lo: int = 1
+    perc_hi: int = 99
+    av_filter_flag: bool = True
+    av_savgol_window: int = 10
+    av_savgol_poly: int = 4
+    print_report: bool = False
+    return_value: bool = True
+
+
+def default_cardiac_cycle_config() -> CardiacCycleConfig:
+    return CardiacCycleConfig()
+
+
+def default_peak_detection_config() -> PeakDetectionConfig:
+    return PeakDetectionConfig()

@@ -9,8 +9,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -30,7 +32,6 @@ static const int kCtlInts = 2 + 2 * kMaxGroups + 2;   // next_pair, pairs_done, 
 #ifndef TEEFLOW_PITCH0
 #define TEEFLOW_PITCH0 1024
 #endif
-static const size_t kRingSmem = (size_t)kWarpsPerCta * kRingB;   // dynamic shared memory of a launch with two-iteration strips
 static const int kPitches[] = {TEEFLOW_PITCH0, 2048, 4096};  // instantiated plane pitches (float2 elements): W <= pitch
 static const size_t kPlaneAlign = (size_t)kPlanes * 4096 * sizeof(float2);   // Lay<4096>::ROWB, a multiple of the others
 
@@ -44,12 +45,28 @@ static step_kernel_t step_kernel_for(int pitch) {
     }
 }
 
+typedef void (*flow_kernel_t)(const EngineParams);
+static flow_kernel_t flow_kernel_for(int pitch) {
+    switch (pitch) {
+        case TEEFLOW_PITCH0: return tvl1_flow_kernel<TEEFLOW_PITCH0>;
+        case 2048: return tvl1_flow_kernel<2048>;
+        case 4096: return tvl1_flow_kernel<4096>;
+        default: return nullptr;
+    }
+}
+
 struct teeflow_engine {
     teeflow_params p;
     int device = 0;
     int num_sms = 0;
-    int ctas_per_sm[3] = {1, 1, 1};   // per instantiated pitch
-    int ctas_per_sm_ring[3] = {1, 1, 1};   // ... with the two-iteration strips' shared-memory ring
+    int ctas_per_sm[3] = {1, 1, 1};   // per instantiated pitch (stepped kernel)
+    int ctas_per_sm_flow[3] = {1, 1, 1};   // ... (dataflow kernel)
+    int stepped = 0;                  // 1: one launch per phase step (profiling / A-B); 0: one dataflow launch per run
+    Task* tasks = nullptr;            // [kTaskRing] task descriptors of the dataflow scheduler
+    FlowCtl* flow_ctl = nullptr;
+    int* h_flow_order = nullptr;      // mapped pinned host memory: completion order written by the running kernel
+    int* d_flow_order = nullptr;      // its device address
+    size_t cap_flow_order = 0;
     std::string err;
     // workspace (grown on demand)
     size_t cap_frames = 0, cap_pyr_stride = 0;
@@ -71,7 +88,7 @@ struct teeflow_engine {
     const float* wase_w = nullptr;  // caller-owned [H][W][2] weight map (nullptr: no background compensation)
     int wase_H = 0, wase_W = 0;
     // analysis scratch (teeflow_analyze_clip)
-    size_t an_cap = 0; int an_frames = 0, an_H = 0, an_W = 0;
+    size_t an_cap = 0, an_frames_cap = 0; int an_frames = 0, an_H = 0, an_W = 0;
     float *an_mag = nullptr, *an_ang = nullptr;
     double *an_rad = nullptr, *an_long = nullptr, *an_cent = nullptr;
     FrameStats* an_stats = nullptr;
@@ -80,7 +97,7 @@ struct teeflow_engine {
     unsigned long long* an_keys = nullptr;
     unsigned long long* prep_mm = nullptr; size_t prep_cap = 0;
     // saliency scratch (teeflow_saliency_fine_grained), sized for kSalChunk frames
-    size_t sal_cap = 0;
+    size_t sal_cap_px = 0, sal_cap_int = 0;   // capacities in pixels / integral-image entries per frame
     uint8_t *sal_g0 = nullptr, *sal_g1 = nullptr, *sal_on = nullptr, *sal_off = nullptr;
     float *sal_prefix = nullptr, *sal_integ = nullptr;
     uint16_t *sal_son = nullptr, *sal_soff = nullptr;
@@ -155,6 +172,22 @@ static int level_geometry(const teeflow_params& p, int H, int W, int* Hs, int* W
     return L;
 }
 
+static int query_occupancy(teeflow_engine* h) {
+    for (int i = 0; i < 3; ++i) {
+        int occ = 0;
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_for(kPitches[i]), kThreads, 0));
+        if (occ < 1) return fail(h, TEEFLOW_ERR_CUDA, "tvl1_step_kernel cannot be resident on this device");
+        h->ctas_per_sm[i] = occ;
+        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, flow_kernel_for(kPitches[i]), kThreads, 0));
+        if (occ < 1) return fail(h, TEEFLOW_ERR_CUDA, "tvl1_flow_kernel cannot be resident on this device");
+        h->ctas_per_sm_flow[i] = occ;
+    }
+    int coop = 0;
+    CU_TRY(h, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    if (!coop) h->stepped = 1;        // no residency guarantee for the dataflow kernel: one launch per phase step instead
+    return TEEFLOW_OK;
+}
+
 extern "C" {
 
 void teeflow_default_params(teeflow_params* p) {
@@ -167,6 +200,29 @@ void teeflow_default_params(teeflow_params* p) {
 int teeflow_abi_version(void) { return TEEFLOW_ABI_VERSION; }
 
 const char* teeflow_last_error(teeflow_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+// everything of teeflow_create that can fail after the handle exists; the caller destroys the handle on error
+static int create_resources(teeflow_engine* h) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+    int rc = query_occupancy(h);
+    if (rc) return rc;
+    CU_TRY(h, cudaMallocHost(&h->h_done, sizeof(int) * 4));
+    CU_TRY(h, cudaMalloc(&h->ctl, sizeof(int) * kCtlInts));
+    for (auto& ev : h->ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU_TRY(h, cudaEventCreate(&h->ev_t0));
+    CU_TRY(h, cudaEventCreate(&h->ev_t1));
+    CU_TRY(h, cudaEventCreate(&h->ev_tp));
+    CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int g = 0; g < kMaxGroups - 1; ++g) {
+        CU_TRY(h, cudaStreamCreateWithFlags(&h->group_stream[g], cudaStreamNonBlocking));
+        for (int w = 0; w < 2; ++w) CU_TRY(h, cudaEventCreateWithFlags(&h->ev_group[w][g], cudaEventDisableTiming));
+    }
+    return TEEFLOW_OK;
+}
 
 int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
     if (!out) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "out handle pointer is NULL");
@@ -185,32 +241,16 @@ int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
     if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "out of host memory");
     h->p = pp;
     h->device = device;
-    CU_TRY(h, cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CU_TRY(h, cudaGetDeviceProperties(&prop, device));
-    h->num_sms = prop.multiProcessorCount;
-    for (int i = 0; i < 3; ++i) {
-        int occ = 0;
-        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_for(kPitches[i]), kThreads, 0));
-        if (occ < 1) { delete h; return fail(nullptr, TEEFLOW_ERR_CUDA, "tvl1_step_kernel cannot be resident on this device"); }
-        h->ctas_per_sm[i] = occ;
-        CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel_for(kPitches[i]), kThreads, kRingSmem));
-        h->ctas_per_sm_ring[i] = std::max(occ, 1);
-    }
-    CU_TRY(h, cudaMallocHost(&h->h_done, sizeof(int) * 4));
-    CU_TRY(h, cudaMalloc(&h->ctl, sizeof(int) * kCtlInts));
-    for (auto& ev : h->ev) CU_TRY(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU_TRY(h, cudaEventCreate(&h->ev_t0));
-    CU_TRY(h, cudaEventCreate(&h->ev_t1));
-    CU_TRY(h, cudaEventCreate(&h->ev_tp));
-    CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    CU_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int g = 0; g < kMaxGroups - 1; ++g) {
-        CU_TRY(h, cudaStreamCreateWithFlags(&h->group_stream[g], cudaStreamNonBlocking));
-        for (int w = 0; w < 2; ++w) CU_TRY(h, cudaEventCreateWithFlags(&h->ev_group[w][g], cudaEventDisableTiming));
+    rc = create_resources(h);
+    if (rc) {                          // streams, events, pinned memory created so far go with the handle
+        const std::string msg = h->err;
+        teeflow_destroy(h);
+        g_last_error = msg;
+        return rc;
     }
     if (const char* e = getenv("TEEFLOW_GROUPS")) h->groups = std::max(1, std::min(atoi(e), kMaxGroups));
     if (const char* e = getenv("TEEFLOW_SPEC")) h->spec_factor = std::max(0.0f, (float)atof(e));
+    if (const char* e = getenv("TEEFLOW_STEPPED")) h->stepped = atoi(e) != 0 || h->stepped;
     *out = h;
     return TEEFLOW_OK;
 }
@@ -220,7 +260,8 @@ int teeflow_destroy(teeflow_handle h) {
     cudaSetDevice(h->device);
     cudaFree(h->pyrI); cudaFree(h->pyrG);
     cudaFree(h->planes_raw); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
-    cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg);
+    cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg); cudaFree(h->tasks); cudaFree(h->flow_ctl);
+    if (h->h_flow_order) cudaFreeHost(h->h_flow_order);
     cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
     cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
     cudaFree(h->an_edges); cudaFree(h->an_freq); cudaFree(h->prep_mm);
@@ -229,7 +270,7 @@ int teeflow_destroy(teeflow_handle h) {
     cudaFree(h->ccl_L); cudaFree(h->ccl_area); cudaFree(h->ccl_touch); cudaFree(h->ccl_ncomp);
     cudaFree(h->ccl_sr); cudaFree(h->ccl_sc); cudaFree(h->ccl_best);
     cudaFree(h->stage_in); cudaFree(h->stage_f32); cudaFree(h->stage_f16);
-    cudaFreeHost(h->h_done);
+    if (h->h_done) cudaFreeHost(h->h_done);
     if (h->h_order) cudaFreeHost(h->h_order);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -247,7 +288,7 @@ int teeflow_destroy(teeflow_handle h) {
 }
 
 static double* param_slot_d(teeflow_params& p, const char* key) {
-    if (!strcmp(key, "spec_factor")) return nullptr;   // handle-level knob, see teeflow_set_param
+    if (!strcmp(key, "spec_factor") || !strcmp(key, "stepped")) return nullptr;   // handle-level knobs, see teeflow_set_param
     if (!strcmp(key, "tau")) return &p.tau;
     if (!strcmp(key, "lambda")) return &p.lambda;
     if (!strcmp(key, "theta")) return &p.theta;
@@ -272,6 +313,10 @@ int teeflow_set_param(teeflow_handle h, const char* key, double value) {
         h->spec_factor = (float)value;
         return TEEFLOW_OK;
     }
+    if (!strcmp(key, "stepped")) {       // 1: one launch per phase step (profiling); results never depend on it
+        h->stepped = value != 0;
+        return TEEFLOW_OK;
+    }
     teeflow_params np = h->p;
     if (double* d = param_slot_d(np, key)) *d = value;
     else if (int32_t* i = param_slot_i(np, key)) {
@@ -287,6 +332,7 @@ int teeflow_set_param(teeflow_handle h, const char* key, double value) {
 int teeflow_get_param(teeflow_handle h, const char* key, double* value) {
     if (!h || !key || !value) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
     if (!strcmp(key, "spec_factor")) { *value = h->spec_factor; return TEEFLOW_OK; }
+    if (!strcmp(key, "stepped")) { *value = h->stepped; return TEEFLOW_OK; }
     if (double* d = param_slot_d(h->p, key)) { *value = *d; return TEEFLOW_OK; }
     if (int32_t* i = param_slot_i(h->p, key)) { *value = (double)*i; return TEEFLOW_OK; }
     return fail(h, TEEFLOW_ERR_BAD_ARG, "unknown parameter '%s'", key);
@@ -471,10 +517,34 @@ static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_strid
 
 // host_f32 / host_f16 (optional): host mirrors of the output buffers; the flow of a finished pair is copied out while
 // the other pairs are still being solved (a frame pair is an independent unit, its result is final once written)
+static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                          int64_t frame_stride, const int32_t* pair_a, const int32_t* pair_b, const int32_t* out_index,
+                          const int32_t* dup_index, int n_pairs, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
+                          cudaStream_t stream, float* host_f32, void* host_f16);
+
+// An error inside the launch loop must not return while step kernels are still queued on the group streams or
+// early device-to-host copies are still writing into the caller's buffers: drain everything first.
 static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n_frames, int H, int W,
                      int64_t frame_stride, const int32_t* pair_a, const int32_t* pair_b, const int32_t* out_index,
                      const int32_t* dup_index, int n_pairs, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
                      cudaStream_t stream, float* host_f32 = nullptr, void* host_f16 = nullptr) {
+    const int rc = run_pairs_impl(h, frames_dev, dtype, n_frames, H, W, frame_stride, pair_a, pair_b, out_index, dup_index,
+                                  n_pairs, flow_f32_dev, flow_f16_dev, out_scale, stream, host_f32, host_f16);
+    if (rc != TEEFLOW_OK && h) {
+        const std::string msg = h->err;
+        cudaStreamSynchronize(stream);
+        for (int g = 0; g < kMaxGroups - 1; ++g) if (h->group_stream[g]) cudaStreamSynchronize(h->group_stream[g]);
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+        cudaGetLastError();
+        h->err = msg; g_last_error = msg;
+    }
+    return rc;
+}
+
+static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                          int64_t frame_stride, const int32_t* pair_a, const int32_t* pair_b, const int32_t* out_index,
+                          const int32_t* dup_index, int n_pairs, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
+                          cudaStream_t stream, float* host_f32, void* host_f16) {
     if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
     if (!frames_dev || !pair_a || !pair_b || !out_index || !dup_index)
         return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL frames or pair list");
@@ -586,11 +656,7 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     // every launch fills all resident CTA slots; giving each group 1/G of them, so that the groups' launches are
     // co-resident on every SM all the time, was measured slower (1037 vs 1134 pairs/s): few slots at a time sweeping
     // the same image rows keeps DRAM pages open
-    // two-iteration strips stage their rows in dynamic shared memory; launches without them take none, so the
-    // other phases keep the whole L1 (their spills and gathers live there)
-    const bool ring = P.spec_factor > 0.0f;
-    const size_t smem = ring ? kRingSmem : 0;
-    const int grid = h->num_sms * (ring ? h->ctas_per_sm_ring[pitch_i] : h->ctas_per_sm[pitch_i]);
+    const int grid = h->num_sms * h->ctas_per_sm[pitch_i];
 
     // ---- slot table: the first S pairs start at the coarsest level, parity 0
     {
@@ -612,14 +678,106 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
         CU_TRY(h, cudaEventRecord(h->ev_tp, stream));
     }
 
-    // ---- super-steps.  The slots are split into groups that step on separate streams: while one group's launch
-    // drains (its last strips, the launch gap, the next launch's prologue) the other group's strips keep the SMs
-    // busy.  The host keeps two chunks of launches in flight per stream and polls the done counter of the chunk
-    // before; finished slots make their warps exit at once, so an over-issued launch costs microseconds.
+    // early copy-out of finished pairs (host-buffer entry points)
+    const bool copy_out = host_f32 || host_f16;
+    const size_t npx_out = (size_t)H * W;
+    int n_copied = 0;
+    auto copy_pair = [&](int pair) -> cudaError_t {
+        const int idx[2] = {out_index[pair], dup_index[pair]};
+        for (int k = 0; k < 2; ++k) {
+            if (idx[k] < 0) continue;
+            cudaError_t e = cudaSuccess;
+            if (host_f32) e = cudaMemcpyAsync(host_f32 + (size_t)idx[k] * npx_out * 2, flow_f32_dev + (size_t)idx[k] * npx_out * 2,
+                                              npx_out * 8, cudaMemcpyDeviceToHost, h->copy_stream);
+            if (e == cudaSuccess && host_f16)
+                e = cudaMemcpyAsync((char*)host_f16 + (size_t)idx[k] * npx_out * 4, (char*)flow_f16_dev + (size_t)idx[k] * npx_out * 4,
+                                    npx_out * 4, cudaMemcpyDeviceToHost, h->copy_stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    auto finish_stats = [&](long long launches, int grid_ctas, int applied, int discarded) -> int {
+        CU_TRY(h, cudaEventElapsedTime(&h->st.device_ms, h->ev_t0, h->ev_t1));
+        CU_TRY(h, cudaEventElapsedTime(&h->st.pyramid_ms, h->ev_t0, h->ev_tp));
+        CU_TRY(h, cudaEventElapsedTime(&h->st.solver_ms, h->ev_tp, h->ev_t1));
+        h->st.double_steps = applied; h->st.double_steps_discarded = discarded;
+        h->st.solver_launches = launches;
+        h->st.kernel_launches += launches;
+        h->st.n_slots = S;
+        h->st.grid_ctas = grid_ctas;
+        return TEEFLOW_OK;
+    };
+
+    // ---- dataflow scheduler: ONE cooperative launch solves every pair (tvl1_flow_kernel); the host only watches the
+    // completion list the kernel writes into mapped pinned memory and copies finished flows out meanwhile
+    if (!h->stepped && h->n_launch_events == 0) {
+        if (!h->tasks) CU_TRY(h, cudaMalloc(&h->tasks, sizeof(Task) * kTaskRing));
+        if (!h->flow_ctl) CU_TRY(h, cudaMalloc(&h->flow_ctl, sizeof(FlowCtl)));
+        if ((size_t)n_pairs > h->cap_flow_order) {
+            h->cap_flow_order = 0;
+            if (h->h_flow_order) cudaFreeHost(h->h_flow_order);
+            h->h_flow_order = nullptr;
+            CU_TRY(h, cudaHostAlloc(&h->h_flow_order, sizeof(int) * n_pairs, cudaHostAllocMapped));
+            CU_TRY(h, cudaHostGetDevicePointer(&h->d_flow_order, h->h_flow_order, 0));
+            h->cap_flow_order = (size_t)n_pairs;
+        }
+        for (int i = 0; i < n_pairs; ++i) h->h_flow_order[i] = -1;
+        const unsigned items0 = (unsigned)P.lv[L - 1].pw_items;      // strips of a level-init task at the coarsest level
+        std::vector<Task> t0((size_t)S);
+        memset(t0.data(), 0, sizeof(Task) * t0.size());
+        for (int s = 0; s < S; ++s) {
+            Task& t = t0[s];
+            t.seq = (unsigned)s + 1u; t.first = (unsigned)s * items0; t.n_items = items0; t.pair = s; t.slot = s;
+            t.bits = (unsigned)PH_LEVEL_INIT | ((unsigned)(L - 1) << 8);
+        }
+        FlowCtl c0;
+        memset(&c0, 0, sizeof(c0));
+        c0.alloc = ((unsigned long long)S << 32) | ((unsigned long long)S * items0);
+        c0.next_pair = S;
+        CU_TRY(h, cudaMemsetAsync(h->tasks, 0, sizeof(Task) * kTaskRing, stream));
+        CU_TRY(h, cudaMemcpyAsync(h->tasks, t0.data(), sizeof(Task) * S, cudaMemcpyHostToDevice, stream));
+        CU_TRY(h, cudaMemcpyAsync(h->flow_ctl, &c0, sizeof(c0), cudaMemcpyHostToDevice, stream));
+        CU_TRY(h, cudaStreamSynchronize(stream));                     // t0 / c0 are host temporaries
+        CU_TRY(h, cudaEventRecord(h->ev_tp, stream));
+        EngineParams Pf = P;
+        Pf.tasks = h->tasks; Pf.flow = h->flow_ctl;
+        Pf.spec_stats = &h->flow_ctl->spec_applied;
+        Pf.host_done = copy_out ? h->d_flow_order : nullptr;
+        Pf.watchdog_cycles = 20000000000ll;                           // ~10 s at 2 GHz: a hang becomes an error code
+        const int grid_f = h->num_sms * h->ctas_per_sm_flow[pitch_i];
+        void* args[] = {(void*)&Pf};
+        CU_TRY(h, cudaLaunchCooperativeKernel((const void*)flow_kernel_for(pitch), dim3((unsigned)grid_f), dim3(kThreads), args, 0, stream));
+        CU_TRY(h, cudaEventRecord(h->ev_t1, stream));
+        if (copy_out) {
+            volatile int* order = h->h_flow_order;
+            for (;;) {
+                while (n_copied < n_pairs && order[n_copied] >= 0) CU_TRY(h, copy_pair(order[n_copied++]));
+                if (n_copied == n_pairs) break;
+                const cudaError_t q = cudaEventQuery(h->ev_t1);
+                if (q == cudaSuccess) break;
+                if (q != cudaErrorNotReady) return fail(h, TEEFLOW_ERR_CUDA, "dataflow kernel failed: %s", cudaGetErrorString(q));
+                std::this_thread::sleep_for(std::chrono::microseconds(50));
+            }
+        }
+        CU_TRY(h, cudaStreamSynchronize(stream));
+        FlowCtl c1;
+        CU_TRY(h, cudaMemcpy(&c1, h->flow_ctl, sizeof(c1), cudaMemcpyDeviceToHost));
+        if (c1.abort) return fail(h, TEEFLOW_ERR_STATE, c1.abort == 1 ? "dataflow scheduler watchdog: a warp waited too long for a task"
+                                                                       : "dataflow scheduler lost the task ring");
+        if (c1.pairs_done < n_pairs) return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", c1.pairs_done, n_pairs);
+        if (copy_out) {
+            for (; n_copied < n_pairs; ++n_copied) {
+                const int pair = h->h_flow_order[n_copied];
+                if (pair < 0 || pair >= n_pairs) return fail(h, TEEFLOW_ERR_STATE, "completion list is corrupt at %d", n_copied);
+                CU_TRY(h, copy_pair(pair));
+            }
+            CU_TRY(h, cudaStreamSynchronize(h->copy_stream));
+        }
+        return finish_stats(1, grid_f, c1.spec_applied, c1.spec_discarded);
+    }
+
+    // ---- super-steps (stepped scheduler).  The slots are split into groups that step on separate streams: while one group's launch
     const step_kernel_t step_kernel = step_kernel_for(pitch);
-    CU_TRY(h, cudaFuncSetAttribute(step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   ring ? (int)((grid / h->num_sms) * (kRingSmem + 4096) * 100 / (228 * 1024)) + 1
-                                        : (int)cudaSharedmemCarveoutDefault));
     const int chunk = 16;
     EngineParams Pg[kMaxGroups];
     cudaStream_t gs[kMaxGroups];
@@ -640,31 +798,13 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     bool done = false;
     volatile int* hd = h->h_done;
     hd[0] = hd[1] = 0;
-    // early copy-out of finished pairs (host-buffer entry points)
-    const bool copy_out = host_f32 || host_f16;
-    const size_t npx_out = (size_t)H * W;
-    int n_copied = 0;
-    auto copy_pair = [&](int pair) -> cudaError_t {
-        const int idx[2] = {out_index[pair], dup_index[pair]};
-        for (int k = 0; k < 2; ++k) {
-            if (idx[k] < 0) continue;
-            cudaError_t e = cudaSuccess;
-            if (host_f32) e = cudaMemcpyAsync(host_f32 + (size_t)idx[k] * npx_out * 2, flow_f32_dev + (size_t)idx[k] * npx_out * 2,
-                                              npx_out * 8, cudaMemcpyDeviceToHost, h->copy_stream);
-            if (e == cudaSuccess && host_f16)
-                e = cudaMemcpyAsync((char*)host_f16 + (size_t)idx[k] * npx_out * 4, (char*)flow_f16_dev + (size_t)idx[k] * npx_out * 4,
-                                    npx_out * 4, cudaMemcpyDeviceToHost, h->copy_stream);
-            if (e != cudaSuccess) return e;
-        }
-        return cudaSuccess;
-    };
     while (!done) {
         if (step > max_steps) return fail(h, TEEFLOW_ERR_STATE, "scheduler exceeded %lld steps", max_steps);
         for (int k = 0; k < chunk; ++k, ++step)
             for (int g = 0; g < G; ++g) {
                 const bool timed = g == 0 && step < h->n_launch_events;
                 if (timed && step == 0) CU_TRY(h, cudaEventRecord(h->ev_launch[0], gs[0]));
-                step_kernel<<<grid, kThreads, smem, gs[g]>>>(Pg[g], (int)(step & 1));
+                step_kernel<<<grid, kThreads, 0, gs[g]>>>(Pg[g], (int)(step & 1));
                 if (timed) { CU_TRY(h, cudaEventRecord(h->ev_launch[step + 1], gs[0])); h->n_launches_timed = (int)step + 1; }
             }
         CU_TRY(h, cudaGetLastError());
@@ -714,19 +854,9 @@ static int run_pairs(teeflow_engine* h, const void* frames_dev, int dtype, int n
     step *= G;
     for (int i = 0; i < h->n_launches_timed; ++i)
         CU_TRY(h, cudaEventElapsedTime(&h->launch_ms[i], h->ev_launch[i], h->ev_launch[i + 1]));
-    CU_TRY(h, cudaEventElapsedTime(&h->st.device_ms, h->ev_t0, h->ev_t1));
-    CU_TRY(h, cudaEventElapsedTime(&h->st.pyramid_ms, h->ev_t0, h->ev_tp));
-    CU_TRY(h, cudaEventElapsedTime(&h->st.solver_ms, h->ev_tp, h->ev_t1));
-    {
-        int sp[2] = {0, 0};
-        CU_TRY(h, cudaMemcpy(sp, h->ctl + 2 + 2 * kMaxGroups, sizeof(sp), cudaMemcpyDeviceToHost));
-        h->st.double_steps = sp[0]; h->st.double_steps_discarded = sp[1];
-    }
-    h->st.solver_launches = step;
-    h->st.kernel_launches += step;
-    h->st.n_slots = S;
-    h->st.grid_ctas = grid;
-    return TEEFLOW_OK;
+    int sp[2] = {0, 0};
+    CU_TRY(h, cudaMemcpy(sp, h->ctl + 2 + 2 * kMaxGroups, sizeof(sp), cudaMemcpyDeviceToHost));
+    return finish_stats(step, grid, sp[0], sp[1]);
 }
 
 extern "C" {
@@ -871,6 +1001,7 @@ int teeflow_prepare_frames(teeflow_handle h, const uint8_t* rgb_dev, int n_frame
     cudaStream_t stream = (cudaStream_t)stream_v;
     CU_TRY(h, cudaSetDevice(h->device));
     if ((size_t)n_frames * 2 > h->prep_cap) {
+        h->prep_cap = 0;
         CU_TRY(h, regrow(h->prep_mm, (size_t)n_frames * 2));
         h->prep_cap = (size_t)n_frames * 2;
     }
@@ -897,14 +1028,17 @@ int teeflow_saliency_fine_grained(teeflow_handle h, const uint8_t* rgb_dev, int 
     cudaStream_t stream = (cudaStream_t)stream_v;
     CU_TRY(h, cudaSetDevice(h->device));
     const size_t npx = (size_t)H * W, nint = (size_t)(H + 1) * (W + 1);
-    if (nint > h->sal_cap) {
-        h->sal_cap = 0;
-        CU_TRY(h, regrow(h->sal_g0, npx * kSalChunk)); CU_TRY(h, regrow(h->sal_g1, npx * kSalChunk));
-        CU_TRY(h, regrow(h->sal_on, npx * kSalChunk)); CU_TRY(h, regrow(h->sal_off, npx * kSalChunk));
-        CU_TRY(h, regrow(h->sal_prefix, npx * kSalChunk)); CU_TRY(h, regrow(h->sal_integ, nint * kSalChunk));
-        CU_TRY(h, regrow(h->sal_son, npx * kSalChunk)); CU_TRY(h, regrow(h->sal_soff, npx * kSalChunk));
+    if (npx > h->sal_cap_px || nint > h->sal_cap_int) {
+        // grow to the maximum of both measures seen so far: a later frame shape with fewer integral entries but more
+        // pixels (3 x 3333 then 100 x 100) must not run on the smaller allocation
+        const size_t cpx = std::max(npx, h->sal_cap_px), cint = std::max(nint, h->sal_cap_int);
+        h->sal_cap_px = 0; h->sal_cap_int = 0;
+        CU_TRY(h, regrow(h->sal_g0, cpx * kSalChunk)); CU_TRY(h, regrow(h->sal_g1, cpx * kSalChunk));
+        CU_TRY(h, regrow(h->sal_on, cpx * kSalChunk)); CU_TRY(h, regrow(h->sal_off, cpx * kSalChunk));
+        CU_TRY(h, regrow(h->sal_prefix, cpx * kSalChunk)); CU_TRY(h, regrow(h->sal_integ, cint * kSalChunk));
+        CU_TRY(h, regrow(h->sal_son, cpx * kSalChunk)); CU_TRY(h, regrow(h->sal_soff, cpx * kSalChunk));
         if (!h->sal_max) CU_TRY(h, regrow(h->sal_max, (size_t)kSalChunk));
-        h->sal_cap = nint;
+        h->sal_cap_px = cpx; h->sal_cap_int = cint;
     }
     const dim3 blk(32, 8);
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>(kSalChunk, (size_t)INT_MAX / npx));   // 32-bit pixel index per chunk
@@ -1073,14 +1207,17 @@ int teeflow_analyze_clip(teeflow_handle h, const void* flow_f16_dev, const uint8
     CU_TRY(h, cudaSetDevice(h->device));
     const size_t npx = (size_t)H * W, need = npx * nframes;
     if (need > h->an_cap) {
+        h->an_cap = 0;
         CU_TRY(h, regrow(h->an_mag, need)); CU_TRY(h, regrow(h->an_ang, need));
         CU_TRY(h, regrow(h->an_rad, need)); CU_TRY(h, regrow(h->an_long, need));
         h->an_cap = need;
     }
-    if (nframes > h->an_frames || !h->an_stats) {
+    if ((size_t)nframes > h->an_frames_cap) {
+        h->an_frames_cap = 0;
         CU_TRY(h, regrow(h->an_stats, (size_t)nframes)); CU_TRY(h, regrow(h->an_anghist, (size_t)nframes * kAngBins));
         CU_TRY(h, regrow(h->an_cent, (size_t)nframes * 2)); CU_TRY(h, regrow(h->an_ranks, (size_t)nframes * 12));
         CU_TRY(h, regrow(h->an_keys, (size_t)nframes * 12));
+        h->an_frames_cap = (size_t)nframes;
     }
     h->an_frames = nframes; h->an_H = H; h->an_W = W;
     CU_TRY(h, cudaMemcpyAsync(h->an_cent, centroids_host, sizeof(double) * 2 * nframes, cudaMemcpyHostToDevice, stream));
@@ -1162,7 +1299,11 @@ int teeflow_analysis_histogram(teeflow_handle h, int quantity, const void* edges
     const bool f64 = quantity >= 2;
     const size_t esz = f64 ? 8 : 4;
     if (!h->an_edges) CU_TRY(h, cudaMalloc(&h->an_edges, 8 * 8193));
-    if ((size_t)nframes * nbins > h->an_freq_cap) { CU_TRY(h, regrow(h->an_freq, (size_t)nframes * nbins)); h->an_freq_cap = (size_t)nframes * nbins; }
+    if ((size_t)nframes * nbins > h->an_freq_cap) {
+        h->an_freq_cap = 0;
+        CU_TRY(h, regrow(h->an_freq, (size_t)nframes * nbins));
+        h->an_freq_cap = (size_t)nframes * nbins;
+    }
     CU_TRY(h, cudaMemcpyAsync(h->an_edges, edges_host, esz * (nbins + 1), cudaMemcpyHostToDevice, stream));
     CU_TRY(h, cudaMemsetAsync(h->an_freq, 0, sizeof(unsigned long long) * nframes * nbins, stream));
     const int chunks = std::max(1, std::min((int)((npx + 256 * 8 - 1) / (256 * 8)), 64));

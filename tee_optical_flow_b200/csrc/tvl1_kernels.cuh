@@ -15,7 +15,10 @@
 
 namespace teeflow {
 
-constexpr int kThreads = 256;  // threads per CTA
+#ifndef TEEFLOW_THREADS
+#define TEEFLOW_THREADS 128
+#endif
+constexpr int kThreads = TEEFLOW_THREADS;  // threads per CTA
 constexpr int kWarpsPerCta = kThreads / 32;
 #ifndef TEEFLOW_IW
 #define TEEFLOW_IW 31
@@ -25,19 +28,11 @@ constexpr int kIW = TEEFLOW_IW;        // inner strip: output columns per warp (
 #define TEEFLOW_STRIP_ROWS 20
 #endif
 constexpr int kIR = TEEFLOW_STRIP_ROWS;   // inner strip: rows per warp (measured 16: 1215, 20: 1245, 24: 1241, 32: 1233, 40: 1200 pairs/s)
-constexpr int kIW2 = 28;       // two-iteration strip: output columns per warp (lanes 1..28; lane 0 / 29 / 30 halo columns)
+constexpr int kIW2 = 29;       // two-iteration strip: output columns per warp (lanes 1..29; lane 0 / 30 / 31 halo columns)
 #ifndef TEEFLOW_STRIP2_ROWS
-#define TEEFLOW_STRIP2_ROWS 24
+#define TEEFLOW_STRIP2_ROWS 32
 #endif
-constexpr int kIR2 = TEEFLOW_STRIP2_ROWS;   // two-iteration strip: rows per warp (3 extra rows are computed per strip)
-#ifndef TEEFLOW_RING2
-#define TEEFLOW_RING2 4
-#endif
-constexpr int kRing2 = TEEFLOW_RING2;       // image rows staged per warp (shared-memory ring): rows r-1, r + look-ahead
-constexpr int kSegPx = 34;                  // staged columns per plane row: [x0 - 2, x0 + 32)
-constexpr int kSegB = kSegPx * 8;           // 272 bytes = 17 x 16-byte copies
-constexpr int kStageB = 5 * kSegB;          // U, CA, CB, PX, PY of one image row
-constexpr int kRingB = kRing2 * kStageB;    // per warp
+constexpr int kIR2 = TEEFLOW_STRIP2_ROWS;   // two-iteration strip: rows per warp (3 extra row steps per strip)
 #ifndef TEEFLOW_POINT_ROWS
 #define TEEFLOW_POINT_ROWS 16
 #endif
@@ -233,13 +228,13 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
     float2* row = SB + L::at(0, y0, x);          // plane 0 of row y0; planes / rows at constant offsets
     const unsigned oU = (PL_U + (unsigned)ucur) * (unsigned)PITCH;
     // the flow / I0 of the next row are fetched while the current row's gather runs (one row ahead)
-    float2 u_n = __ldg(row + oU);
+    float2 u_n = row[oU];
     float i0_n = __ldg(I0 + (unsigned)(y0 * g.W + x));
     for (int y = y0; y < y1; ++y) {
         const unsigned q = (unsigned)(y * g.W + x);
         const float2 u = u_n;
         const float i0 = i0_n;
-        if (y + 1 < y1) { u_n = __ldg(row + oU + L::ROW); i0_n = __ldg(I0 + q + (unsigned)g.W); }
+        if (y + 1 < y1) { u_n = row[oU + L::ROW]; i0_n = __ldg(I0 + q + (unsigned)g.W); }
         const float mx = (float)x + u.x, my = (float)y + u.y;
         const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic, P.negzero);
         const float Ix2 = w.y * w.y, Iy2 = w.z * w.z;
@@ -275,10 +270,10 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
                 if (interior) {                          // x-2 .. x+2 inside the image: one pointer + immediates
                     const float* q = row + xs[0];
 #pragma unroll
-                    for (int dx = 0; dx < 5; ++dx) v[dx] = __ldg(q + 2 * dx);
+                    for (int dx = 0; dx < 5; ++dx) v[dx] = q[2 * dx];
                 } else {
 #pragma unroll
-                    for (int dx = 0; dx < 5; ++dx) v[dx] = __ldg(row + xs[dx]);
+                    for (int dx = 0; dx < 5; ++dx) v[dx] = row[xs[dx]];
                 }
                 TF_MED_SORT5(v)
             };
@@ -317,7 +312,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = __ldg(SB + L::at(pUs, yy, xx));
+                    const float2 t = SB[L::at(pUs, yy, xx)];
                     v[(dy + 1) * 3 + dx + 1] = t.x;
                     w[(dy + 1) * 3 + dx + 1] = t.y;
                 }
@@ -490,7 +485,7 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     const char* pp = base + ((int)PL_PX + pcur) * PB;   // PX[pcur]; PY[pcur] at + 2 PB (partners: ^ PB)
     const char* pc = base + (int)PL_CA * PB;            // CA; CB at + PB
 
-    auto ld = [](const char* p, int off) { return __ldg(reinterpret_cast<const float2*>(p + off)); };
+    auto ld = [](const char* p, int off) { return *reinterpret_cast<const float2*>(p + off); };
     // ping-pong partner plane: one XOR when PB is a power of two (address bits of row / plane / column are disjoint),
     // else an add of +-PB
     const int du = ucur ? -PB : PB, dp = pcur ? -PB : PB;
@@ -589,29 +584,24 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     return err;
 }
 
-// ---- asynchronous staging (LDGSTS): 16 bytes per lane, global -> shared, bypassing L1 and the register file
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // PH_INNER2: TWO primal-dual iterations in one pass over the state (temporal blocking): 40 bytes read and 24
-// written per pixel for two iterations instead of one.  A warp owns kIW2 = 28 output columns and kIR2 rows; its 32
-// lanes sit on columns x0-1 .. x0+30 and it walks rows y0-1 .. y1+1, a four-stage software pipeline per row r:
+// written per pixel for two iterations instead of one.  Register-only: a warp owns kIW2 = 29 output columns and kIR2
+// rows; its 32 lanes sit on columns x0-1 .. x0+30 and it walks rows y0-1 .. y1+1, a four-stage software pipeline
+// per row step r:
 //   A(r)   u'  = first-iteration  u of row r        (all lanes)          needs p(r), p(r-1), u(r), coefficients(r)
-//   B(r-1) p'  = first-iteration  p of row r-1      (lanes 0..30)        needs u'(r-1), u'(r)
+//   B(r-1) p'  = first-iteration  p of row r-1      (lanes 0..30)        needs u'(r-1), u'(r), p(r-1)
 //   C(r-1) u'' = second-iteration u of row r-1      (lanes 1..30)        needs u'(r-1), p'(r-1), p'(r-2), coeff.(r-1)
 //   D(r-2) p'' = second-iteration p of row r-2      (lanes 1..29)        needs u''(r-2), u''(r-1), p'(r-2)
-// Only u'(r-1), p'(r-1 / r-2) and u''(r-2) are carried in registers; the input rows live in a per-warp ring of
-// shared memory filled two rows ahead by 16-byte asynchronous copies, so rows r and r-1 are read where needed
-// instead of being kept.  Image borders follow the single-iteration rules in BOTH iterations; halo lanes outside
-// the image compute on whatever the margins hold and are masked where a neighbour reads them.  Error sums of both
-// iterations are returned (err1: |u' - u|^2, err2: |u'' - u'|^2 over the owned pixels).
+// Carried in registers between row steps: u'(r-1), p'(r-2), u''(r-2), the inputs p / coefficients of row r-1, and
+// the loads of row r+1 (issued one step ahead, like the single-iteration op) -- no shared memory, no barrier, so the
+// pass costs the other phases nothing (the round-1 version staged rows in a shared-memory ring whose carve-out took
+// the L1 the other phases live in).  Horizontal neighbours come by warp shuffle.  Image borders follow the
+// single-iteration rules in BOTH iterations; halo lanes outside the image read a clamped column, compute on
+// whatever it holds and are masked where a neighbour reads them.  Error sums of both iterations are returned
+// (err1: |u' - u|^2, err2: |u'' - u'|^2 over the owned pixels).
 template <int PITCH>
 __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int ucur, int pcur, int slot, int strip,
-                                          int lane, unsigned char* ring, double& err1, double& err2) {
+                                          int lane, double& err1, double& err2) {
     using L = Lay<PITCH>;
     constexpr int PB = (int)L::PB, ROWB = (int)L::ROWB;
     const LevelGeom& g = P.lv[level];
@@ -624,43 +614,34 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
     const bool owner = lane >= 1 && lane <= kIW2 && c < W;    // lane owns the outputs of its column
     const unsigned right_mask = (c + 1 < W) ? 0xffffffffu : 0u;   // forward x-difference exists
     const unsigned not_col0 = (c > 0) ? 0xffffffffu : 0u;         // a left neighbour exists
+    const unsigned shfl_left = (lane != 0 && c > 0) ? 0xffffffffu : 0u;   // ... and it sits in lane - 1
+    const bool lane0_left = (lane == 0 && c > 0);             // lane 0 loads the input px of column c - 1 itself
     const bool strip_at_x0 = (x0 == 0);                       // warp-uniform
     const bool first_col = (c == 0);
-    const int rs = max(y0 - 2, 0);                            // first staged row (only its py is used when y0 >= 2)
     const int ra = max(y0 - 1, 0);                            // first row of stage A
-    const int re = min(y1 + 1, H - 1);                        // last staged row / last row of stage A
+    const int re = min(y1 + 1, H - 1);                        // last row of stage A
     const int qb = min(y1, H - 1);                            // last row of stages B and C
+    const int cc = clampi(c, 0, W - 1);                       // dead lanes read a legal address
 
-    const char* sbase = reinterpret_cast<const char*>(slot_base(P, slot));
-    // staged columns [x0 - 2, x0 + 32), 16-byte aligned (x0 is even); the strips at x0 = 0 stage [0, 34) instead
-    // and read two columns further left in the segment (their lane 0, column -1, is a dead halo lane)
-    const int shift = strip_at_x0 ? 2 : 0;
-    const char* seg = sbase + ((size_t)rs * (size_t)ROWB + (size_t)(x0 - 2 + shift + kXMargin) * 8u);
-    const char* cu = seg + ucur * PB + lane * 16;                    // copy sources, this lane's 16 bytes (lane < 17)
-    const char* cc = seg + (int)PL_CA * PB + lane * 16;              // CA; CB at + PB
-    const char* cq = seg + ((int)PL_PX + pcur) * PB + lane * 16;     // PX[pcur]; PY[pcur] at + 2 PB
-    // stores: this lane's column in the partner planes; wu1 -> row r-1 (u''), wq2 -> row r-2 (p''), r = ra at first
-    char* wu1 = const_cast<char*>(sbase) + ((ptrdiff_t)(ra - 1) * ROWB + (ucur ^ 1) * PB + (c + kXMargin) * 8);
-    char* wq2 = const_cast<char*>(sbase) + ((ptrdiff_t)(ra - 2) * ROWB + ((int)PL_PX + (pcur ^ 1)) * PB + (c + kXMargin) * 8);
-    const uint32_t ring_cp = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
-    const unsigned char* ring_rd = ring + (lane + 1 - shift) * 8;    // this lane's column inside a staged segment
+    const char* base = reinterpret_cast<const char*>(slot_base(P, slot)) + ((size_t)ra * (size_t)ROWB + (size_t)(cc + kXMargin) * 8u);
+    const char* pu = base + ucur * PB;                  // U[ucur] of row r
+    const char* pp = base + ((int)PL_PX + pcur) * PB;   // PX[pcur]; PY[pcur] at + 2 PB
+    const char* pc = base + (int)PL_CA * PB;            // CA; CB at + PB
+    const int du = ucur ? -PB : PB, dp = pcur ? -PB : PB;     // ping-pong partner planes (the results go there)
 
-    const int n_rows = re - rs + 1;
-    int issued = 0;
-    auto issue_row = [&](int stage) {            // stage and issued are warp-uniform
-        if (issued < n_rows && lane < 17) {
-            const uint32_t d = ring_cp + stage * kStageB;
-            cp_async16(d, cu);
-            cp_async16(d + kSegB, cc);
-            cp_async16(d + 2 * kSegB, cc + PB);
-            cp_async16(d + 3 * kSegB, cq);
-            cp_async16(d + 4 * kSegB, cq + 2 * PB);
-        }
-        cp_async_commit();                       // an empty group keeps the group count per row constant
-        ++issued; cu += ROWB; cc += ROWB; cq += ROWB;
-    };
-    auto rd = [&](int stage, int plane, int off) {
-        return *reinterpret_cast<const float2*>(ring_rd + stage * kStageB + plane * kSegB + off);
+    auto ld = [](const char* p, int off) { return *reinterpret_cast<const float2*>(p + off); };
+    auto st = [](const char* p, int off, float2 v) { *reinterpret_cast<float2*>(const_cast<char*>(p) + off) = v; };
+    auto load_row = [&](int rows_ahead) {
+        const int d = rows_ahead * ROWB;
+        InnerRow r;
+        r.u = ld(pu, d);
+        r.ca = ld(pc, d);
+        r.cb = ld(pc, d + PB);
+        r.px = ld(pp, d);
+        r.py = ld(pp, d + 2 * PB);
+        r.pxl = make_float2(0.f, 0.f);
+        if (lane0_left) r.pxl = ld(pp, d - 8);
+        return r;
     };
     auto diff_x = [&](float2 v) {                // forward x-difference (zero in the last image column)
         const float2 d = sub2(make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1)), v);
@@ -670,36 +651,33 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
         return make_float2(and_mask(__shfl_up_sync(0xffffffffu, v.x, 1), not_col0),
                            and_mask(__shfl_up_sync(0xffffffffu, v.y, 1), not_col0));
     };
-    auto st = [](char* p, int off, float2 v) { *reinterpret_cast<float2*>(p + off) = v; };
     auto sq_norm = [](float2 a, float2 b) { const float2 d = sub2(a, b); const float2 q = mul2(d, d); return (double)(q.x + q.y); };
 
-#pragma unroll
-    for (int k = 0; k < kRing2; ++k) issue_row(k);
-
     double e1 = 0.0, e2 = 0.0;
-    float2 u1p = make_float2(0.f, 0.f);                       // u'  of row r-1
-    float2 p1x = make_float2(0.f, 0.f), p1y = p1x;            // p'  of row r-2 (when a step starts)
-    float2 u2p = make_float2(0.f, 0.f);                       // u'' of row r-2 (when a step starts)
     const float2 zero2 = make_float2(0.f, 0.f);
+    float2 u1p = zero2;                                       // u'  of row r-1
+    float2 p1x = zero2, p1y = zero2;                          // p'  of row r-2 (when a step starts)
+    float2 u2p = zero2;                                       // u'' of row r-2 (when a step starts)
+    float2 ca_p = zero2, cb_p = zero2, px_p = zero2;          // inputs of row r-1
+    float2 py_p = ra >= 1 ? ld(pp, 2 * PB - ROWB) : zero2;
+    InnerRow nxt = load_row(0);                               // row ra
 
+#pragma unroll 1
     for (int r = ra; r <= y1 + 1; ++r) {
-        const int i = r - rs;                                  // staged row index of r
-        const int sc = i % kRing2, sp = (i + kRing2 - 1) % kRing2;   // ring stages of rows r and r-1
         const bool has_a = r <= re;                            // row r exists (warp-uniform)
+        const InnerRow row = nxt;
+        if (r < re) nxt = load_row(1);                         // row r + 1 is in flight while this step computes
         float2 u1 = zero2;
         if (has_a) {
-            cp_async_wait<kRing2 - 2>();
-            __syncwarp();
-            InnerRow row;
-            row.u = rd(sc, 0, 0); row.ca = rd(sc, 1, 0); row.cb = rd(sc, 2, 0);
-            row.px = rd(sc, 3, 0); row.py = rd(sc, 4, 0);
-            const float2 l = rd(sc, 3, -8);
-            row.pxl = make_float2(and_mask(l.x, not_col0), and_mask(l.y, not_col0));
-            const float2 pyu = r >= 1 ? rd(sp, 4, 0) : zero2;
-            VStep v = estimate_v_fast(row, K);
-            if (v.bad) v.d = estimate_v_exact(row, v);
-            u1 = add2(add2(row.u, v.d), theta_div_px(row, row.pxl, pyu, strip_at_x0, first_col && r > 0, K));
-            if (owner && r >= y0 && r < y1) e1 += sq_norm(u1, row.u);
+            // A(r): estimateV + divergence(p) + estimateU, first iteration
+            InnerRow in = row;
+            in.pxl = make_float2(and_or(__shfl_up_sync(0xffffffffu, row.px.x, 1), shfl_left, row.pxl.x),
+                                 and_or(__shfl_up_sync(0xffffffffu, row.px.y, 1), shfl_left, row.pxl.y));
+            const float2 pyu = r >= 1 ? py_p : zero2;
+            VStep v = estimate_v_fast(in, K);
+            if (v.bad) v.d = estimate_v_exact(in, v);
+            u1 = add2(add2(in.u, v.d), theta_div_px(in, in.pxl, pyu, strip_at_x0, first_col && r > 0, K));
+            if (owner && r >= y0 && r < y1) e1 += sq_norm(u1, in.u);
         }
         const int q = r - 1;
         float2 n1x = zero2, n1y = zero2, u2 = zero2;          // p' and u'' of row q
@@ -707,18 +685,17 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
             // B(q): forwardGradient(u') + estimateDualVariables, first iteration
             const float2 ux = diff_x(u1p);
             const float2 uy = has_a ? sub2(u1, u1p) : zero2;
-            const float2 px0 = rd(sp, 3, 0), py0 = rd(sp, 4, 0);
-            if (!dual_update_fast(ux, uy, px0, py0, K, n1x, n1y)) dual_update_exact(ux, uy, px0, py0, K, n1x, n1y);
+            if (!dual_update_fast(ux, uy, px_p, py_p, K, n1x, n1y)) dual_update_exact(ux, uy, px_p, py_p, K, n1x, n1y);
             if (q >= y0) {
                 // C(q): estimateV + divergence(p') + estimateU, second iteration
-                InnerRow row;
-                row.u = u1p; row.ca = rd(sp, 1, 0); row.cb = rd(sp, 2, 0); row.px = n1x; row.py = n1y;
-                row.pxl = left_of(n1x);
+                InnerRow in;
+                in.u = u1p; in.ca = ca_p; in.cb = cb_p; in.px = n1x; in.py = n1y;
+                in.pxl = left_of(n1x);
                 const float2 pyu = q >= 1 ? p1y : zero2;
-                VStep v = estimate_v_fast(row, K);
-                if (v.bad) v.d = estimate_v_exact(row, v);
-                u2 = add2(add2(u1p, v.d), theta_div_px(row, row.pxl, pyu, strip_at_x0, first_col && q > 0, K));
-                if (owner && q < y1) { st(wu1, 0, u2); e2 += sq_norm(u2, u1p); }
+                VStep v = estimate_v_fast(in, K);
+                if (v.bad) v.d = estimate_v_exact(in, v);
+                u2 = add2(add2(u1p, v.d), theta_div_px(in, in.pxl, pyu, strip_at_x0, first_col && q > 0, K));
+                if (owner && q < y1) { st(pu, du - ROWB, u2); e2 += sq_norm(u2, u1p); }
             }
         }
         const int q2 = r - 2;
@@ -728,15 +705,12 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
             const float2 uy = (q2 + 1 <= H - 1) ? sub2(u2, u2p) : zero2;
             float2 pxn, pyn;
             if (!dual_update_fast(ux, uy, p1x, p1y, K, pxn, pyn)) dual_update_exact(ux, uy, p1x, p1y, K, pxn, pyn);
-            if (owner) { st(wq2, 0, pxn); st(wq2, 2 * PB, pyn); }
+            if (owner) { st(pp, dp - 2 * ROWB, pxn); st(pp, dp - 2 * ROWB + 2 * PB, pyn); }
         }
         u1p = u1; p1x = n1x; p1y = n1y; u2p = u2;
-        wu1 += ROWB; wq2 += ROWB;
-        __syncwarp();                                          // every lane has read row r-1: refill its stage
-        if (i >= 1) issue_row(sp);
+        ca_p = row.ca; cb_p = row.cb; px_p = row.px; py_p = row.py;
+        pu += ROWB; pp += ROWB; pc += ROWB;
     }
-    cp_async_wait<0>();
-    __syncwarp();                                              // the ring may be refilled by this warp's next strip
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         e1 += __shfl_down_sync(0xffffffffu, e1, o);
@@ -809,16 +783,101 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
     }
 }
 
+// ------------------------------------------------------------------------------------------- strip dispatch
+// Loads of the slot planes are PLAIN loads (never ld.global.nc): in the dataflow kernel a plane is rewritten by other
+// SMs between two reads of the same launch, and only ordinary loads are covered by the acquire fence a warp executes
+// after it has been handed a strip (the fence also drops the SM's stale L1 lines).  Read-only inputs (pyramid, WASE
+// weights, cubic table) keep the non-coherent path.
+#ifndef TEEFLOW_PHASE_MASK
+#define TEEFLOW_PHASE_MASK 0xffu
+#endif
+// TEEFLOW_PHASE_MASK (analysis builds only): compile a subset of the strip ops, to read one op's register need and
+// SASS in isolation (tools/op_resources.sh); the shipped library has all of them
+__device__ __forceinline__ constexpr bool has_op(int phase) { return ((TEEFLOW_PHASE_MASK >> phase) & 1u) != 0; }
+
+template <int PITCH>
+__device__ __forceinline__ void run_strip(const EngineParams& P, int phase, int level, int ucur, int pcur, int pair,
+                                          float bg, int slot, int strip, int lane, const float4* s_cubic, double& err,
+                                          double& aux) {
+    if (has_op(PH_LEVEL_INIT) && phase == PH_LEVEL_INIT) op_level_init<PITCH>(P, level, ucur, slot, strip, lane);
+    else if (has_op(PH_WARP) && phase == PH_WARP) op_warp<PITCH>(P, level, ucur, pair, slot, strip, lane, s_cubic);
+    else if (has_op(PH_MEDIAN) && phase == PH_MEDIAN) op_median<PITCH>(P, level, ucur, slot, strip, lane);
+    else if (has_op(PH_INNER) && phase == PH_INNER) err = op_inner<PITCH>(P, level, ucur, pcur, slot, strip, lane);
+    else if (has_op(PH_INNER2) && phase == PH_INNER2) op_inner2<PITCH>(P, level, ucur, pcur, slot, strip, lane, err, aux);
+    else if (has_op(PH_WASE) && phase == PH_WASE) op_wase<PITCH>(P, ucur, slot, strip, lane, err, aux);
+    else if (has_op(PH_FINAL) && phase == PH_FINAL) op_final<PITCH>(P, ucur, pair, bg, slot, strip, lane);
+}
+
+// lane 0 records the strip's error partial(s) and takes an arrival ticket of the slot; true for the warp that
+// delivered the last strip of the task
+__device__ __forceinline__ bool strip_arrive(const EngineParams& P, int phase, int slot, int strip, int n_items, int lane,
+                                             double err, double aux) {
+    int last = 0;
+    if (lane == 0) {
+        if (phase == PH_INNER) P.partial[(size_t)slot * P.max_tiles + strip] = err;
+        if (phase == PH_WASE || phase == PH_INNER2) {
+            P.partial[(size_t)slot * P.max_tiles + 2 * strip] = err;
+            P.partial[(size_t)slot * P.max_tiles + 2 * strip + 1] = aux;
+        }
+        __threadfence();
+        const unsigned ticket = atomicAdd(P.arrive + slot, 1u);
+        last = (ticket == (unsigned)n_items - 1u);
+    }
+    return __shfl_sync(0xffffffffu, last, 0) != 0;
+}
+
+// fixed-order (strip order, then a shuffle tree) float64 reduction of a finished task's partials
+__device__ __forceinline__ void reduce_partials(const EngineParams& P, int phase, int slot, int n_items, int lane, double& e,
+                                                double& e2) {
+    e = 0.0; e2 = 0.0;
+    const double* part = P.partial + (size_t)slot * P.max_tiles;
+    if (phase == PH_INNER) {
+        for (int t = lane; t < n_items; t += 32) e += __ldcg(part + t);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
+    } else if (phase == PH_WASE || phase == PH_INNER2) {
+        for (int t = lane; t < n_items; t += 32) { e += __ldcg(part + 2 * t); e2 += __ldcg(part + 2 * t + 1); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            e += __shfl_down_sync(0xffffffffu, e, o);
+            e2 += __shfl_down_sync(0xffffffffu, e2, o);
+        }
+    }
+}
+
+// One finished task -> the slot's next state (lane 0 of the finishing warp).  Returns the pair that was completed by
+// this task (PH_FINAL), or -1.  `spec` points at the two-iteration statistics (applied, discarded).
+__device__ __forceinline__ int next_state(const EngineParams& P, Slot& n, double e, double e2, int* next_pair) {
+    if (n.phase == PH_WASE) {
+        n.bg = (float)(e / e2);          // 0/0 -> NaN, like np.mean of an empty selection
+        P.bg_out[n.pair] = n.bg;
+        n.phase = PH_FINAL;
+        return -1;
+    }
+    if (n.phase == PH_FINAL) {
+        const int finished = n.pair;
+        int* co = P.counters_out + (size_t)n.pair * kMaxLevels * 3;
+        for (int l = 0; l < kMaxLevels; ++l) { co[l * 3] = n.cnt[l][0]; co[l * 3 + 1] = n.cnt[l][1]; co[l * 3 + 2] = n.cnt[l][2]; }
+        const int next = atomicAdd(next_pair, 1);
+        if (next < P.n_pairs) start_pair(P, n, next);
+        else { n.pair = -1; n.phase = PH_IDLE; }
+        return finished;
+    }
+    advance_slot(P, n, e, e2);
+    return -1;
+}
+
 // ------------------------------------------------------------------------------------------- the super-step
+// (stepped scheduler: one launch = one phase of every slot of a group; kept for per-phase timing / profiling and as
+// the A/B reference of the dataflow kernel below -- teeflow_set_param("stepped", 1))
 #ifndef TEEFLOW_MIN_CTAS
-#define TEEFLOW_MIN_CTAS 4
+#define TEEFLOW_MIN_CTAS 6
 #endif
 template <int PITCH>
 __global__ void __launch_bounds__(kThreads, TEEFLOW_MIN_CTAS)
 tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     __shared__ int s_prefix[kMaxSlots + 1];
     __shared__ float4 s_cubic[32];
-    extern __shared__ __align__(16) unsigned char s_ring[];   // [kWarpsPerCta][kRingB] when two-iteration passes are on
 
     // this launch serves the slot group [slot0, slot0 + S): groups run on separate streams so that the tail and
     // the launch gap of one group's step are filled by the other group's strips
@@ -841,13 +900,10 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
         for (int s = tid; s < P.S; s += kThreads)
             if (s_prefix[s + 1] == s_prefix[s]) nxt[s] = cur[s];
 
-#if TEEFLOW_DYNAMIC_ITEMS
     // dynamic distribution: every warp pulls the next strip from a per-launch counter, so strips of unequal cost
     // (inner / median / warp phases mix in one launch) balance out; the counter of the other parity is re-armed.
     // Strips are handed out slot by slot in raster order: at any moment the running warps work on neighbouring
-    // strips of very few slots and sweep the same image rows together, which is what keeps DRAM pages open --
-    // handing out strips interleaved over the slots of the group (so that the ALU-bound median / warp strips of
-    // some slots overlap the HBM-bound inner strips of others) was measured at 897-1053 pairs/s against 1134.
+    // strips of very few slots and sweep the same image rows together, which is what keeps DRAM pages open.
     // The first strip of every warp is its global warp index (no burst of same-address atomics at launch); the
     // counter therefore starts at the number of warps of the grid.
     if (blockIdx.x == 0 && tid == 0) P.item_counter[parity ^ 1] = (int)gridDim.x * kWarpsPerCta;
@@ -858,11 +914,6 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
             item = __shfl_sync(0xffffffffu, item, 0);
         }
         if (item >= total) break;
-#else
-    const int n_warps = gridDim.x * kWarpsPerCta;
-    // CTA-interleaved item order: the 8 warps of a CTA take 8 consecutive strips (shared cache lines)
-    for (int item = blockIdx.x * kWarpsPerCta + (tid >> 5); item < total; item += n_warps) {
-#endif
         int lo = 0, hi = P.S;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_prefix[mid] <= item) lo = mid; else hi = mid; }
         const int strip = item - s_prefix[lo];
@@ -872,67 +923,149 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
         const int n_items = s_prefix[lo + 1] - s_prefix[lo];
 
         double err = 0.0, aux = 0.0;
-        switch (phase) {
-            case PH_LEVEL_INIT: op_level_init<PITCH>(P, level, ucur, slot, strip, lane); break;
-            case PH_WARP: op_warp<PITCH>(P, level, ucur, pair, slot, strip, lane, s_cubic); break;
-            case PH_MEDIAN: op_median<PITCH>(P, level, ucur, slot, strip, lane); break;
-            case PH_INNER: err = op_inner<PITCH>(P, level, ucur, pcur, slot, strip, lane); break;
-            case PH_INNER2: op_inner2<PITCH>(P, level, ucur, pcur, slot, strip, lane, s_ring + (tid >> 5) * kRingB, err, aux); break;
-            case PH_WASE: op_wase<PITCH>(P, ucur, slot, strip, lane, err, aux); break;
-            case PH_FINAL: op_final<PITCH>(P, ucur, pair, sp->bg, slot, strip, lane); break;
-            default: break;
-        }
+        run_strip<PITCH>(P, phase, level, ucur, pcur, pair, sp->bg, slot, strip, lane, s_cubic, err, aux);
         __syncwarp();
-        int last = 0;
-        if (lane == 0) {
-            if (phase == PH_INNER) P.partial[(size_t)slot * P.max_tiles + strip] = err;
-            if (phase == PH_WASE || phase == PH_INNER2) {
-                P.partial[(size_t)slot * P.max_tiles + 2 * strip] = err;
-                P.partial[(size_t)slot * P.max_tiles + 2 * strip + 1] = aux;
-            }
-            __threadfence();
-            const unsigned ticket = atomicAdd(P.arrive + slot, 1u);
-            last = (ticket == (unsigned)n_items - 1u);
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
+        if (strip_arrive(P, phase, slot, strip, n_items, lane, err, aux)) {
             // last strip of this slot for this step: reduce the partials in strip order and advance the slot
             __threadfence();
-            double e = 0.0, e2 = 0.0;
-            if (phase == PH_INNER) {
-                const double* part = P.partial + (size_t)slot * P.max_tiles;
-                for (int t = lane; t < n_items; t += 32) e += __ldcg(part + t);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) e += __shfl_down_sync(0xffffffffu, e, o);
-            } else if (phase == PH_WASE || phase == PH_INNER2) {
-                const double* part = P.partial + (size_t)slot * P.max_tiles;
-                for (int t = lane; t < n_items; t += 32) { e += __ldcg(part + 2 * t); e2 += __ldcg(part + 2 * t + 1); }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    e += __shfl_down_sync(0xffffffffu, e, o);
-                    e2 += __shfl_down_sync(0xffffffffu, e2, o);
-                }
-            }
+            double e, e2;
+            reduce_partials(P, phase, slot, n_items, lane, e, e2);
             if (lane == 0) {
                 Slot n = *sp;
-                if (n.phase == PH_WASE) {
-                    n.bg = (float)(e / e2);          // 0/0 -> NaN, like np.mean of an empty selection
-                    P.bg_out[n.pair] = n.bg;
-                    n.phase = PH_FINAL;
-                } else if (n.phase == PH_FINAL) {
-                    const int finished = n.pair;
-                    int* co = P.counters_out + (size_t)n.pair * kMaxLevels * 3;
-                    for (int l = 0; l < kMaxLevels; ++l) { co[l * 3] = n.cnt[l][0]; co[l * 3 + 1] = n.cnt[l][1]; co[l * 3 + 2] = n.cnt[l][2]; }
-                    const int next = atomicAdd(P.next_pair, 1);
-                    if (next < P.n_pairs) start_pair(P, n, next);
-                    else { n.pair = -1; n.phase = PH_IDLE; }
+                const int finished = next_state(P, n, e, e2, P.next_pair);
+                if (finished >= 0) {
                     __threadfence();
                     P.done_order[atomicAdd(P.pairs_done, 1)] = finished;   // the host copies finished flows out early
-                } else {
-                    advance_slot(P, n, e, e2);
                 }
                 nxt[lo] = n;
                 P.arrive[slot] = 0u;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- dataflow scheduler
+// ONE launch per run: every phase of every slot is a task in a device-side FIFO; a task is published by the warp
+// that retires the last strip of the slot's previous task, so slots advance independently of each other -- no grid
+// barrier, no launch boundary, no host round trip.  Warps take strip tickets from one global counter; tickets map to
+// tasks in publication order (tasks are handed out oldest first: the running warps still sweep neighbouring strips
+// of few slots together, which keeps DRAM pages open).  A warp whose ticket belongs to a task that is not published
+// yet waits for it; that can never deadlock: a task's predecessor (same slot) has smaller tickets, all of which are
+// held by warps that run them, and no strip waits for anything.  The grid is launched cooperatively with exactly the
+// resident CTA count, so every warp is running.  A watchdog (clock64) turns a would-be hang into an error code.
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_v4(void* p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// lane 0 of a finishing warp: append the task that runs slot state `n` next (or the terminal task)
+__device__ __forceinline__ void publish_task(const EngineParams& P, int slot, const Slot& n, int phase, unsigned n_items) {
+    const unsigned long long old = atomicAdd(&P.flow->alloc, (1ull << 32) | (unsigned long long)n_items);
+    const unsigned k = (unsigned)(old >> 32), first = (unsigned)old;
+    Task* t = P.tasks + (k & (kTaskRing - 1u));
+    uint4 hi;
+    hi.x = (unsigned)slot;
+    hi.y = (unsigned)phase | ((unsigned)n.level << 8) | ((unsigned)n.ucur << 16) | ((unsigned)n.pcur << 17);
+    hi.z = __float_as_uint(n.bg);
+    hi.w = 0u;
+    *reinterpret_cast<uint4*>(&t->slot) = hi;
+    __threadfence();                                   // the second half and everything the task reads is visible first
+    st_volatile_v4(t, make_uint4(k + 1u, first, n_items, (unsigned)n.pair));
+}
+
+constexpr unsigned kExitItems = 0x40000000u;   // ticket range of the terminal task: every warp takes one more ticket
+
+template <int PITCH>
+__global__ void __launch_bounds__(kThreads, TEEFLOW_MIN_CTAS)
+tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
+    __shared__ float4 s_cubic[32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 32) s_cubic[tid] = cubic_coeffs(tid);
+    __syncthreads();
+    FlowCtl* const F = P.flow;
+    unsigned kc = 0;                                   // task cursor of this warp: only ever moves forward
+
+    for (;;) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(&F->ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        // ---- which task owns ticket t?  32 descriptors per probe, one per lane
+        unsigned strip = 0, n_items = 0;
+        int pair = 0;
+        for (;;) {
+            const Task* q = P.tasks + ((kc + (unsigned)lane) & (kTaskRing - 1u));
+            const uint4 d = ld_volatile_v4(q);         // seq, first, n_items, pair: one 16-byte store of the publisher
+            const unsigned want = kc + (unsigned)lane + 1u;
+            const bool pub = d.x == want;
+            const unsigned hit = __ballot_sync(0xffffffffu, pub && (t - d.y) < d.z);
+            if (hit) {
+                const int src = __ffs(hit) - 1;
+                kc += (unsigned)src;
+                strip = t - __shfl_sync(0xffffffffu, d.y, src);
+                n_items = __shfl_sync(0xffffffffu, d.z, src);
+                pair = (int)__shfl_sync(0xffffffffu, d.w, src);
+                break;
+            }
+            // a descriptor of a later lap of the ring: this warp lagged kTaskRing tasks behind (cannot happen in practice)
+            if (__any_sync(0xffffffffu, (int)(d.x - want) > 0)) { if (lane == 0) atomicExch(&F->abort, 2); return; }
+            const unsigned unp = __ballot_sync(0xffffffffu, !pub);
+            if (unp == 0u) { kc += 32u; continue; }    // 32 published tasks, all of them before ticket t
+            kc += (unsigned)(__ffs(unp) - 1);          // the first unpublished one: wait until it appears (one lane polls)
+            int give_up = 0;
+            if (lane == 0) {
+                const unsigned* seq = &P.tasks[kc & (kTaskRing - 1u)].seq;
+                const long long t0 = clock64();
+                unsigned ns = 128;
+                while (ld_volatile_u32(seq) != kc + 1u) {
+                    if (*reinterpret_cast<volatile int*>(&F->abort)) { give_up = 1; break; }
+                    if (clock64() - t0 > P.watchdog_cycles) { atomicExch(&F->abort, 1); give_up = 1; break; }
+                    __nanosleep(ns);
+                    if (ns < 2048) ns *= 2;
+                }
+            }
+            if (__shfl_sync(0xffffffffu, give_up, 0)) return;
+        }
+        __threadfence();                               // acquire: what the task's publisher (and its strips) wrote
+        const Task* tk = P.tasks + (kc & (kTaskRing - 1u));
+        const uint4 hi = __ldcg(reinterpret_cast<const uint4*>(&tk->slot));
+        const int slot = (int)hi.x;
+        const int phase = (int)(hi.y & 0xffu), level = (int)((hi.y >> 8) & 0xffu);
+        const int ucur = (int)((hi.y >> 16) & 1u), pcur = (int)((hi.y >> 17) & 1u);
+        if (phase == PH_EXIT) return;
+
+        double err = 0.0, aux = 0.0;
+        run_strip<PITCH>(P, phase, level, ucur, pcur, pair, __uint_as_float(hi.z), slot, (int)strip, lane, s_cubic, err, aux);
+        __syncwarp();
+        if (strip_arrive(P, phase, slot, (int)strip, (int)n_items, lane, err, aux)) {
+            __threadfence();
+            double e, e2;
+            reduce_partials(P, phase, slot, (int)n_items, lane, e, e2);
+            if (lane == 0) {
+                Slot& n = P.slots[0][slot];            // only the warp that retires a slot's task touches its state
+                const int finished = next_state(P, n, e, e2, &F->next_pair);
+                P.arrive[slot] = 0u;
+                bool all_done = false;
+                if (finished >= 0) {
+                    __threadfence();                   // the flow of the finished pair is visible before its index
+                    const int pos = atomicAdd(&F->pairs_done, 1);
+                    P.done_order[pos] = finished;
+                    if (P.host_done) {                 // the host copies finished flows out while the rest is solved
+                        __threadfence_system();
+                        P.host_done[pos] = finished;
+                    }
+                    all_done = (pos + 1 == P.n_pairs);
+                }
+                if (n.phase != PH_IDLE) publish_task(P, slot, n, n.phase, (unsigned)items_of(P, n.phase, n.pair, n.level));
+                if (all_done) publish_task(P, slot, n, PH_EXIT, kExitItems);   // swallows every further ticket
             }
         }
     }

@@ -287,14 +287,23 @@ class TVL1Engine:
         return out.cpu().numpy() if is_np else out
 
     # ------------------------------------------------------------------ WASE background compensation
-    def set_wase_masks(self, bkgd_mask) -> None:
+    def set_wase_masks(self, bkgd_mask, cache: bool = False) -> None:
         """bkgd_comp='WASE' (calculate_optical_flow.py:649-652): `bkgd_mask` is mask_dict['bkgd'], (N, H, W, 2) bool
         for ALL frames (numpy or CUDA torch tensor).  Builds the weight map w = sum_n bkgd[n] on the GPU and makes
-        every following calc subtract the per-pair scalar mean(flow*bkgd != 0).  None switches it off."""
+        every following calc subtract the per-pair scalar mean(flow*bkgd != 0).  None switches it off.
+        cache=True keeps the last weight map keyed by the mask OBJECT (the per-pair wrapper is called with the same
+        mask_dict for every pair of a clip); the caller must not mutate that array in between."""
         import torch
         if bkgd_mask is None:
-            self._wase_w = None
+            if not cache:
+                self._wase_w = None
+                self._wase_key = None
             self._check(self._lib.teeflow_set_wase(self._h, None, 0, 0))
+            return
+        key = (id(bkgd_mask), tuple(bkgd_mask.shape))
+        if cache and getattr(self, "_wase_key", None) == key and getattr(self, "_wase_w", None) is not None:
+            w = self._wase_w
+            self._check(self._lib.teeflow_set_wase(self._h, w.data_ptr(), w.shape[0], w.shape[1]))
             return
         m = bkgd_mask if isinstance(bkgd_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bkgd_mask))
         if m.dim() != 4 or m.shape[-1] != 2:
@@ -307,6 +316,8 @@ class TVL1Engine:
         self._check(self._lib.teeflow_wase_weights(self._h, m.data_ptr(), N, H, W, w.data_ptr(), C.c_void_p(stream)))
         torch.cuda.current_stream(m.device).synchronize()
         self._wase_w = w                      # keep the caller-owned buffer alive
+        self._wase_key = key if cache else None
+        self._wase_ref = bkgd_mask if cache else None   # pins id(): the key cannot be reused by another object
         self._check(self._lib.teeflow_set_wase(self._h, w.data_ptr(), H, W))
 
     def last_backgrounds(self) -> np.ndarray:

@@ -28,3 +28,8 @@ class ConfigurationError(OpticalFlowError):
 
 class EngineUnavailableError(OpticalFlowCalculationError):
     """libteeflow.so is missing / not loadable, or no CUDA device: there is deliberately no CPU fallback."""
+
+
+class SaliencyParityWarning(UserWarning):
+    """The `no_saliency=False` input stage (StaticSaliencyFineGrained) runs a restatement whose parity with
+    cv2.saliency is unpinned; emitted once per process_frames call that uses it."""

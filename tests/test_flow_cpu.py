@@ -1,12 +1,12 @@
-"""CPU tests of the host-side API mirror (flow.py): frame prep arithmetic, chunking, error behaviour that does not
-need a GPU."""
+"""CPU tests of the host-side API mirror (flow.py) -- chunking, metadata, error behaviour that does not need a GPU --
+and of the frame-prep restatement the GPU kernels are checked against (oracle/frame_prep_ref.py)."""
 import numpy as np
 import pytest
 
 
 def test_img2uint8_follows_reference_formula():
     """optical_flow_utils.py:30-31: img_as_ubyte((img - min) / max) -- divides by max, not by the range"""
-    from tee_optical_flow_b200.flow import img2uint8, rgb2gray
+    from oracle.frame_prep_ref import img2uint8, rgb2gray
     rng = np.random.default_rng(0)
     rgb = rng.integers(0, 256, (12, 14, 3), dtype=np.uint8)
     g = rgb2gray(rgb)
@@ -19,7 +19,7 @@ def test_img2uint8_follows_reference_formula():
 
 
 def test_prepare_frames_gray_and_rgb():
-    from tee_optical_flow_b200.flow import prepare_frames
+    from oracle.frame_prep_ref import prepare_frames
     rng = np.random.default_rng(1)
     gray = rng.integers(0, 256, (3, 8, 9), dtype=np.uint8)
     a = prepare_frames(gray)
@@ -48,6 +48,65 @@ def test_process_frames_validates_before_touching_the_gpu():
         process_frames(fr, bkgd_comp='median', frames_are_prepared=True)
     with pytest.raises(ConfigurationError):
         process_frames(fr, bkgd_comp='WASE', frames_are_prepared=True)      # no 'bkgd' mask
+
+
+def test_process_frames_has_no_host_frame_prep_fallback():
+    """unusual dtypes are refused instead of being prepared on the host (north_star: no CPU fallback)"""
+    from tee_optical_flow_b200.exceptions import OpticalFlowCalculationError
+    from tee_optical_flow_b200.flow import process_frames
+    with pytest.raises(OpticalFlowCalculationError, match='uint8'):
+        process_frames(np.zeros((3, 16, 16, 3), np.float32))
+    with pytest.raises(OpticalFlowCalculationError, match='uint8'):
+        process_frames(np.zeros((3, 16, 16), np.uint16))
+
+
+class _Tag:
+    def __init__(self, v): self.value = v
+
+
+class _FakeDicom:
+    """attribute / item access of a pydicom dataset, just enough for extract_dicom_metadata"""
+    def __init__(self, region_dx=None, **attrs):
+        self._region = region_dx
+        for k, v in attrs.items():
+            setattr(self, k, v)
+
+    def __getitem__(self, key):
+        if key == (0x0018, 0x6011) and self._region is not None:
+            return [{'PhysicalDeltaX': _Tag(self._region)}]
+        raise KeyError(key)
+
+
+def test_dicom_metadata_fallback_chain_matches_reference():
+    """calculate_optical_flow.py:315-367: CineRate -> round(1000/FrameTime) -> round(1000/FrameTimeVector[1]); every
+    item independent of the others"""
+    from tee_optical_flow_b200.flow import extract_dicom_metadata
+    md = extract_dicom_metadata(_FakeDicom(region_dx=0.031, CineRate=47))
+    assert md['pixel_spacing'] == 0.031 and md['frame_rate'] == 47 and md['R_wave_data_present'] is False
+    md = extract_dicom_metadata(_FakeDicom(region_dx=0.031, FrameTime='21.5'))
+    assert md['pixel_spacing'] == 0.031 and md['frame_rate'] == np.round(1000 / 21.5)
+    md = extract_dicom_metadata(_FakeDicom(FrameTimeVector=[0, 33.3, 33.3], RWaveTimeVector=[10.0, 800.0]))
+    assert md['pixel_spacing'] is None and md['frame_rate'] == np.round(1000 / 33.3)
+    assert md['R_wave_data_present'] and md['R_times'].tolist() == [10.0, 800.0]
+    md = extract_dicom_metadata(_FakeDicom(region_dx=0.05, FrameTime='0'))      # ZeroDivisionError -> next fallback
+    assert md['pixel_spacing'] == 0.05 and md['frame_rate'] is None
+    md = extract_dicom_metadata(_FakeDicom(RWaveTimeVector=3.5))                # a bare float is not a vector (:344)
+    assert md['R_wave_data_present'] is False
+
+
+def test_process_video_refuses_waveform_files_and_needs_masks(tmp_path):
+    from tee_optical_flow_b200.exceptions import ConfigurationError, DICOMReadError
+    from tee_optical_flow_b200.flow import process_video
+    with pytest.raises(ConfigurationError, match='include_waveforms'):
+        process_video('x.dcm', str(tmp_path / 'o.hdf5'), None, include_waveforms=True, waveform_folder='w')
+    def bad_reader(path):
+        raise IOError('nope')
+    with pytest.raises(DICOMReadError):
+        process_video('x.dcm', str(tmp_path / 'o.hdf5'), None, dicom_reader=bad_reader, mask_fn=lambda *a: {})
+    class DS(_FakeDicom):
+        pixel_array = np.zeros((4, 8, 8), np.uint8)
+    with pytest.raises(ConfigurationError, match='mask_fn'):
+        process_video('x.dcm', str(tmp_path / 'o.hdf5'), None, dicom_reader=lambda p: DS(), mode='RVIO_2class')
 
 
 def test_process_folder_swallows_per_file_errors(tmp_path, caplog):

@@ -9,4 +9,5 @@ import bench
 from tee_optical_flow_b200.synth import make_clip
 
 fr = torch.from_numpy(make_clip(seed=0, n_frames=64, H=600, W=800)).cuda()
-print(json.dumps(bench.phase_probe(fr, 0), indent=1))
+res = bench.phase_probe(fr, 0)
+print(json.dumps(res, indent=1))
