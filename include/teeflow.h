@@ -130,6 +130,11 @@ typedef struct {
  * Returns the number of pairs of the last calc. */
 TEEFLOW_API int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap);
 TEEFLOW_API int teeflow_get_stats(teeflow_handle h, teeflow_stats* out);
+/* Diagnostics of the dataflow scheduler (libraries built with -DTEEFLOW_FLOW_STATS=1 only; returns 0 and zeros
+ * otherwise): out32[i] = warp cycles summed over all warps of the last calc, i = solver phase (1 level-init, 2 warp,
+ * 3 median, 4 inner, 5 final, 6 WASE, 7 two-iteration pass), 9 = waiting for a task to be published, 10 = scheduling
+ * (ticket, descriptor probe, fences, arrival, hand-over); out32[16 + i] = number of such intervals. */
+TEEFLOW_API int teeflow_get_flow_stats(teeflow_handle h, uint64_t* out32);
 /* Diagnostics for the roofline accounting of the individual phases: time the first n (<= 64) solver launches of
  * every following calc with CUDA events on the launching stream (n = 0 switches it off), and fetch the durations
  * (ms) of the last calc.  With one slot group (environment TEEFLOW_GROUPS=1 at teeflow_create) and as many slots as

@@ -235,7 +235,7 @@ def radlong_peak_indices(hi_arr, lo_arr, sys_frames, nframes, smooth_fraction=0.
             true_dia.append([true_sys[-1][1], nframes - 1])
         for i in range(len(true_sys) - 1):
             true_dia.append([true_sys[i][1], true_sys[i + 1][0]])
-    sys_i = []
+    sys_i, kept_sys = [], []
     for start, stop in true_sys:
         if pick_peak_by_subset:
             cand = peak_indexes(filt_lo[start:stop + 1] * -1, peak_thres, min_dist) + start
@@ -243,6 +243,7 @@ def radlong_peak_indices(hi_arr, lo_arr, sys_frames, nframes, smooth_fraction=0.
             cand = [k for k in lo_peaks if start <= k <= stop]
         if len(cand) > 0:
             sys_i.append(int(cand[int(np.argmin([filt_lo[i] for i in cand]))]))
+            kept_sys.append([start, stop])                     # runs without a candidate leave true_sys (:52-56)
         else:
             sys_i.append(int(np.argmin(filt_lo[start:stop]) + start))
     e_i, l_i, a_i = [], [], []
@@ -260,8 +261,73 @@ def radlong_peak_indices(hi_arr, lo_arr, sys_frames, nframes, smooth_fraction=0.
                 dst.append(int(cand[int(np.argmax([filt_hi[i] for i in cand]))]))
             else:
                 dst.append(int(np.argmax(filt_hi[s0:s1]) + s0))
-    return dict(sys=sys_i, e=e_i, l=l_i, a=a_i, true_sys=[list(map(int, s)) for s in true_sys],
+    return dict(sys=sys_i, e=e_i, l=l_i, a=a_i, true_sys=[list(map(int, s)) for s in kept_sys],
                 true_dia=[list(map(int, d)) for d in true_dia])
+
+
+# ------------------------------------------------------------------ peak_detection.py:229-375
+def single_peak_indices(filt_arr, sys_frames, nframes, peak_thres=0.2, min_dist=5, pick_peak_by_subset=False):
+    """calculate_single_peaks with cc_method='angle': FRAME INDICES (sys, e', l', a') of one smoothed curve; systolic
+    peaks are maxima, and the diastole runs come from the systole runs that had a peak."""
+    peaks = peak_indexes(filt_arr, peak_thres, min_dist)
+
+    def best(lo, hi):
+        cand = (peak_indexes(filt_arr[lo:hi + 1], peak_thres, min_dist) + lo) if pick_peak_by_subset else \
+            [k for k in peaks if lo <= k <= hi]
+        if len(cand) > 0:
+            return int(cand[int(np.argmax([filt_arr[i] for i in cand]))]), True
+        return int(np.argmax(filt_arr[lo:hi]) + lo), False
+
+    sys_i, true_sys = [], []
+    for start, stop in sys_frames:
+        i, found = best(int(start), int(stop))
+        sys_i.append(i)
+        if found:
+            true_sys.append([int(start), int(stop)])
+    true_dia = []
+    if len(true_sys) > 0:
+        if true_sys[0][0] > 1:
+            true_dia.append([0, true_sys[0][0] - 1])
+        if true_sys[-1][1] < nframes - 2:
+            true_dia.append([true_sys[-1][1], nframes - 1])
+        for i in range(len(true_sys) - 1):
+            true_dia.append([true_sys[i][1], true_sys[i + 1][0]])
+    e_i, l_i, a_i = [], [], []
+    for start, stop in true_dia:
+        third = np.floor((stop - start) / 3)
+        e0, e1 = int(start), int(start + third)
+        l0 = int(e1 + 1); l1 = int(l0 + third)
+        a0, a1 = int(l1 + 1), int(stop + 1)
+        e_i.append(best(e0, e1)[0]); l_i.append(best(l0, l1)[0]); a_i.append(best(a0, a1)[0])
+    return dict(sys=sys_i, e=e_i, l=l_i, a=a_i, true_sys=true_sys, true_dia=true_dia)
+
+
+# ------------------------------------------------------------------ example_peak_plots.py:124-267
+def clip_indices(flow_f16, label_mask, av_mask, nframes, cc_smooth=0.2, cc_pad=20, single_smooth=0.5, smooth_fraction=0.3,
+                 pad_len=20, peak_thres=0.2, min_dist=5, pick_peak_by_subset=True, av_filter=True):
+    """The reference's downstream chain on a stored clip with its default configs (config.py:13-16, 75-82, 85-95):
+    OpticalFlowDataset.vel_array * mask -> AngleDetector -> calculate_3dhist -> SpectralSmoother ->
+    calculate_single_peaks; calc_AV_centroid -> calculate_3dhist_radlong -> calculate_radlong_peaks (x2).
+    Returns only the integer outcomes plus the waveforms they were computed from."""
+    masked = flow_f16.astype(np.float32) * label_mask
+    ang = angle_mode(masked, nframes)
+    sys_frames, dia_frames = angle_detector_intervals(ang, cc_smooth, cc_pad)
+    _, _, _, _, mag_hi = hist3d(masked, nframes)
+    single = single_peak_indices(spectral_smooth(mag_hi, single_smooth, pad_len), sys_frames, nframes, peak_thres, min_dist,
+                                 pick_peak_by_subset)
+    cent = calc_av_centroid(av_mask, nframes, do_filter=av_filter)
+    rad, lng = comp_magnitude(masked, cent)
+    _, _, rhi, rlo = bidirectional_hist(rad, nframes)
+    _, _, lhi, llo = bidirectional_hist(lng, nframes)
+    kw = dict(smooth_fraction=smooth_fraction, pad_len=pad_len, peak_thres=peak_thres, min_dist=min_dist,
+              pick_peak_by_subset=pick_peak_by_subset)
+    pick = lambda d: {k + '_i': [int(i) for i in d[k]] for k in ('sys', 'e', 'l', 'a')}
+    return {
+        'sys_frames': [[int(a), int(b)] for a, b in sys_frames], 'dia_frames': [[int(a), int(b)] for a, b in dia_frames],
+        'single': pick(single), 'radial': pick(radlong_peak_indices(rhi, rlo, sys_frames, nframes, **kw)),
+        'longitudinal': pick(radlong_peak_indices(lhi, llo, sys_frames, nframes, **kw)),
+        'waveforms': dict(ang_mode=ang, mag_hi=mag_hi, rad_hi=rhi, rad_lo=rlo, long_hi=lhi, long_lo=llo), 'centroids': cent,
+    }
 
 
 # ------------------------------------------------------------------ calculate_optical_flow.py:91-182

@@ -68,6 +68,7 @@ SIGNATURES = {
                                          C.c_void_p]),
     "teeflow_get_counters": (C.c_int, [C.c_void_p, _i32p, C.c_int]),
     "teeflow_get_stats": (C.c_int, [C.c_void_p, C.POINTER(TeeflowStats)]),
+    "teeflow_get_flow_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "teeflow_level_sizes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _i32p, _i32p]),
     "teeflow_prepare_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "teeflow_clean_masks": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,

@@ -64,6 +64,8 @@ struct teeflow_engine {
     int stepped = 0;                  // 1: one launch per phase step (profiling / A-B); 0: one dataflow launch per run
     Task* tasks = nullptr;            // [kTaskRing] task descriptors of the dataflow scheduler
     FlowCtl* flow_ctl = nullptr;
+    unsigned long long* flow_stats = nullptr;   // [32] device, diagnostic builds
+    unsigned long long flow_stats_host[32] = {0};
     int* h_flow_order = nullptr;      // mapped pinned host memory: completion order written by the running kernel
     int* d_flow_order = nullptr;      // its device address
     size_t cap_flow_order = 0;
@@ -260,7 +262,7 @@ int teeflow_destroy(teeflow_handle h) {
     cudaSetDevice(h->device);
     cudaFree(h->pyrI); cudaFree(h->pyrG);
     cudaFree(h->planes_raw); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
-    cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg); cudaFree(h->tasks); cudaFree(h->flow_ctl);
+    cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg); cudaFree(h->tasks); cudaFree(h->flow_ctl); cudaFree(h->flow_stats);
     if (h->h_flow_order) cudaFreeHost(h->h_flow_order);
     cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
     cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
@@ -711,8 +713,12 @@ static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, 
     // ---- dataflow scheduler: ONE cooperative launch solves every pair (tvl1_flow_kernel); the host only watches the
     // completion list the kernel writes into mapped pinned memory and copies finished flows out meanwhile
     if (!h->stepped && h->n_launch_events == 0) {
+        if ((unsigned)P.max_tiles > kTaskItemsMax || n_pairs > kTaskPairsMax)
+            return fail(h, TEEFLOW_ERR_BAD_SHAPE, "run too large for the dataflow scheduler's task descriptors");
         if (!h->tasks) CU_TRY(h, cudaMalloc(&h->tasks, sizeof(Task) * kTaskRing));
         if (!h->flow_ctl) CU_TRY(h, cudaMalloc(&h->flow_ctl, sizeof(FlowCtl)));
+        if (!h->flow_stats) CU_TRY(h, cudaMalloc(&h->flow_stats, sizeof(unsigned long long) * 32));
+        CU_TRY(h, cudaMemsetAsync(h->flow_stats, 0, sizeof(unsigned long long) * 32, stream));
         if ((size_t)n_pairs > h->cap_flow_order) {
             h->cap_flow_order = 0;
             if (h->h_flow_order) cudaFreeHost(h->h_flow_order);
@@ -727,8 +733,9 @@ static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, 
         memset(t0.data(), 0, sizeof(Task) * t0.size());
         for (int s = 0; s < S; ++s) {
             Task& t = t0[s];
-            t.seq = (unsigned)s + 1u; t.first = (unsigned)s * items0; t.n_items = items0; t.pair = s; t.slot = s;
-            t.bits = (unsigned)PH_LEVEL_INIT | ((unsigned)(L - 1) << 8);
+            t.seq = (unsigned)s + 1u; t.first = (unsigned)s * items0;
+            t.what = items0 | ((unsigned)PH_LEVEL_INIT << 20) | ((unsigned)(L - 1) << 24);
+            t.who = (unsigned)s | ((unsigned)s << 9);
         }
         FlowCtl c0;
         memset(&c0, 0, sizeof(c0));
@@ -743,6 +750,7 @@ static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, 
         Pf.tasks = h->tasks; Pf.flow = h->flow_ctl;
         Pf.spec_stats = &h->flow_ctl->spec_applied;
         Pf.host_done = copy_out ? h->d_flow_order : nullptr;
+        Pf.flow_stats = h->flow_stats;
         Pf.watchdog_cycles = 20000000000ll;                           // ~10 s at 2 GHz: a hang becomes an error code
         const int grid_f = h->num_sms * h->ctas_per_sm_flow[pitch_i];
         void* args[] = {(void*)&Pf};
@@ -762,6 +770,7 @@ static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, 
         CU_TRY(h, cudaStreamSynchronize(stream));
         FlowCtl c1;
         CU_TRY(h, cudaMemcpy(&c1, h->flow_ctl, sizeof(c1), cudaMemcpyDeviceToHost));
+        CU_TRY(h, cudaMemcpy(h->flow_stats_host, h->flow_stats, sizeof(h->flow_stats_host), cudaMemcpyDeviceToHost));
         if (c1.abort) return fail(h, TEEFLOW_ERR_STATE, c1.abort == 1 ? "dataflow scheduler watchdog: a warp waited too long for a task"
                                                                        : "dataflow scheduler lost the task ring");
         if (c1.pairs_done < n_pairs) return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", c1.pairs_done, n_pairs);
@@ -954,6 +963,12 @@ int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap) {
             CU_TRY(h, cudaMemcpy(counters, h->counters, sizeof(int) * (size_t)n * kMaxLevels * 3, cudaMemcpyDeviceToHost));
     }
     return n;
+}
+
+int teeflow_get_flow_stats(teeflow_handle h, uint64_t* out32) {
+    if (!h || !out32) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
+    for (int i = 0; i < 32; ++i) out32[i] = h->flow_stats_host[i];
+    return TEEFLOW_FLOW_STATS;
 }
 
 int teeflow_get_stats(teeflow_handle h, teeflow_stats* out) {

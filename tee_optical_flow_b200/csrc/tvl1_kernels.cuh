@@ -25,7 +25,7 @@ constexpr int kWarpsPerCta = kThreads / 32;
 #endif
 constexpr int kIW = TEEFLOW_IW;        // inner strip: output columns per warp (lane 31 = right halo column)
 #ifndef TEEFLOW_STRIP_ROWS
-#define TEEFLOW_STRIP_ROWS 20
+#define TEEFLOW_STRIP_ROWS 32
 #endif
 constexpr int kIR = TEEFLOW_STRIP_ROWS;   // inner strip: rows per warp (measured 16: 1215, 20: 1245, 24: 1241, 32: 1233, 40: 1200 pairs/s)
 constexpr int kIW2 = 29;       // two-iteration strip: output columns per warp (lanes 1..29; lane 0 / 30 / 31 halo columns)
@@ -37,6 +37,21 @@ constexpr int kIR2 = TEEFLOW_STRIP2_ROWS;   // two-iteration strip: rows per war
 #define TEEFLOW_POINT_ROWS 16
 #endif
 constexpr int kPR = TEEFLOW_POINT_ROWS;   // pointwise strip: rows per warp, 32 columns (measured 8: 1243, 12: 1250, 16: 1264, 24: 1244 pairs/s)
+#ifndef TEEFLOW_INNER_UNROLL
+#define TEEFLOW_INNER_UNROLL 1
+#endif
+constexpr int kInnerUnroll = TEEFLOW_INNER_UNROLL;   // rows per trip of the single-iteration loop (1 halves its code)
+#ifndef TEEFLOW_WARP_PF
+#define TEEFLOW_WARP_PF 0
+#endif
+constexpr int kWarpPF = TEEFLOW_WARP_PF;   // warp op: tap rows pulled into L2 ahead of the gather window (0: off)
+#ifndef TEEFLOW_LOAD_DEP
+#define TEEFLOW_LOAD_DEP 0
+#endif
+#ifndef TEEFLOW_PF_ROWS
+#define TEEFLOW_PF_ROWS 4
+#endif
+constexpr int kPF = TEEFLOW_PF_ROWS;   // inner iteration: rows ahead of the current one that are pulled into L2 (0: off)
 #ifndef TEEFLOW_DYNAMIC_ITEMS
 #define TEEFLOW_DYNAMIC_ITEMS 1
 #endif
@@ -170,6 +185,8 @@ __device__ __forceinline__ int items_of(const EngineParams& P, int phase, int pa
     return phase == PH_INNER ? P.lv[level].in_items : P.lv[level].pw_items;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // ------------------------------------------------------------------------------------------------ strip ops
 // Slot planes live in the row-interleaved constant-pitch layout of struct Lay (tvl1_device.cuh).
 __device__ __forceinline__ float2* slot_base(const EngineParams& P, int slot) {
@@ -228,14 +245,20 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
     float2* row = SB + L::at(0, y0, x);          // plane 0 of row y0; planes / rows at constant offsets
     const unsigned oU = (PL_U + (unsigned)ucur) * (unsigned)PITCH;
     // the flow / I0 of the next row are fetched while the current row's gather runs (one row ahead)
-    float2 u_n = row[oU];
+    float2 u_n = __ldcg(row + oU);
     float i0_n = __ldg(I0 + (unsigned)(y0 * g.W + x));
     for (int y = y0; y < y1; ++y) {
         const unsigned q = (unsigned)(y * g.W + x);
         const float2 u = u_n;
         const float i0 = i0_n;
-        if (y + 1 < y1) { u_n = row[oU + L::ROW]; i0_n = __ldg(I0 + q + (unsigned)g.W); }
+        if (y + 1 < y1) { u_n = __ldcg(row + oU + L::ROW); i0_n = __ldg(I0 + q + (unsigned)g.W); }
         const float mx = (float)x + u.x, my = (float)y + u.y;
+        if (kWarpPF > 0) {
+            // the flow is smooth: the window of the next pixel rows sits (almost) straight below this one, so the tap
+            // row that enters it kWarpPF rows from now is pulled into L2 already (4 taps x 16 bytes per lane)
+            const int pr = min(max((int)my + 2 + kWarpPF, 0), g.H - 1), pcx = min(max((int)mx - 1, 0), g.W - 1);
+            prefetch_l2(G1 + (unsigned)(pr * g.W + pcx));
+        }
         const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic, P.negzero);
         const float Ix2 = w.y * w.y, Iy2 = w.z * w.z;
         row[PL_CA * PITCH] = make_float2(w.y, w.z);
@@ -485,7 +508,7 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     const char* pp = base + ((int)PL_PX + pcur) * PB;   // PX[pcur]; PY[pcur] at + 2 PB (partners: ^ PB)
     const char* pc = base + (int)PL_CA * PB;            // CA; CB at + PB
 
-    auto ld = [](const char* p, int off) { return *reinterpret_cast<const float2*>(p + off); };
+    auto ld = [](const char* p, int off) { return __ldcg(reinterpret_cast<const float2*>(p + off)); };
     // ping-pong partner plane: one XOR when PB is a power of two (address bits of row / plane / column are disjoint),
     // else an add of +-PB
     const int du = ucur ? -PB : PB, dp = pcur ? -PB : PB;
@@ -498,8 +521,8 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         else return const_cast<char*>(p) + dp;
     };
     auto st = [](char* p, int off, float2 v) { *reinterpret_cast<float2*>(p + off) = v; };
-    auto load_row = [&](int rows_ahead) {
-        const int d = rows_ahead * ROWB;
+    auto load_row = [&](int rows_ahead, int dep = 0) {
+        const int d = rows_ahead * ROWB + dep;
         InnerRow r;
         r.u = ld(pu, d);
         r.ca = ld(pc, d);
@@ -509,6 +532,22 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         r.pxl = make_float2(0.f, 0.f);
         if (lane0_left) r.pxl = ld(pp, d - 8);   // only lane 0 of a strip that does not start at x = 0
         return r;
+    };
+    // `landed(row)` is 0, computed from every load of `row` through a mask the compiler cannot see through.  Adding it
+    // to the addresses of the NEXT batch of loads makes that batch wait until this one has arrived.  Without it the
+    // hardware's counting scoreboards decide: when ptxas lets the new loads share a scoreboard with the previous
+    // batch, the first use of the previous batch waits for the NEW loads as well -- a whole DRAM round trip per row
+    // with nothing overlapped (ncu: one MUFU.RCP held 21 % of all stall samples of the run).
+    auto landed = [&](const InnerRow& r) {
+        return (int)((__float_as_uint(r.u.x) | __float_as_uint(r.ca.x) | __float_as_uint(r.cb.x) |
+                      __float_as_uint(r.px.x) | __float_as_uint(r.py.x)) & (TEEFLOW_LOAD_DEP ? P.zero_mask : 0u));
+    };
+    // The register look-ahead is one row (~1.5 us of work per warp); under load a DRAM access takes about as long, and
+    // with the other phases' warps on the SM too few bytes are in flight (the first use of the next row's loads was
+    // the kernel's top stall).  Rows further ahead are therefore pulled into L2 -- no registers, five instructions.
+    auto prefetch_row = [&](int rows_ahead) {
+        const int d = rows_ahead * ROWB;
+        prefetch_l2(pu + d); prefetch_l2(pc + d); prefetch_l2(pc + d + PB); prefetch_l2(pp + d); prefetch_l2(pp + d + 2 * PB);
     };
     // left neighbour's px: by shuffle, lane 0 takes the value it loaded itself (zero at the image border)
     auto left_px = [&](const InnerRow& r) {
@@ -526,6 +565,10 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     if (y0 > 0) pyu = ld(pp, 2 * PB - ROWB);
     const InnerRow cur = load_row(0);
     InnerRow nxt = load_row(1);                  // row y0 + 1 <= H: inside the image or the first pad row
+    if (kPF > 0) {
+#pragma unroll
+        for (int k = 2; k < kPF; ++k) if (y0 + k < y1) prefetch_row(k);
+    }
 
     float2 un = estimate_u_px(cur, left_px(cur), pyu, strip_at_x0, first_col && y0 > 0, K);
     if (owner) {
@@ -537,10 +580,11 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     float2 px_c = cur.px, py_c = cur.py;
 
     // rows y0 .. y1-2: row y+1 belongs to this strip (u_new stored, error counted); row y+2 <= H is prefetched
-#pragma unroll 2
+#pragma unroll kInnerUnroll
     for (int y = y0; y < y1 - 1; ++y) {
         const InnerRow row = nxt;                // row y+1 (already in flight)
-        nxt = load_row(2);
+        nxt = load_row(2, landed(row));
+        if (kPF > 0 && y + kPF < y1) prefetch_row(kPF);
         // u_new of row y+1, then forwardGradient(u_new) + estimateDualVariables of row y -- fast forms
         VStep v = estimate_v_fast(row, K);
         const float2 tdv = theta_div_px(row, left_px(row), py_c, strip_at_x0, first_col, K);
@@ -629,10 +673,10 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
     const char* pc = base + (int)PL_CA * PB;            // CA; CB at + PB
     const int du = ucur ? -PB : PB, dp = pcur ? -PB : PB;     // ping-pong partner planes (the results go there)
 
-    auto ld = [](const char* p, int off) { return *reinterpret_cast<const float2*>(p + off); };
+    auto ld = [](const char* p, int off) { return __ldcg(reinterpret_cast<const float2*>(p + off)); };
     auto st = [](const char* p, int off, float2 v) { *reinterpret_cast<float2*>(const_cast<char*>(p) + off) = v; };
-    auto load_row = [&](int rows_ahead) {
-        const int d = rows_ahead * ROWB;
+    auto load_row = [&](int rows_ahead, int dep = 0) {
+        const int d = rows_ahead * ROWB + dep;
         InnerRow r;
         r.u = ld(pu, d);
         r.ca = ld(pc, d);
@@ -642,6 +686,14 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
         r.pxl = make_float2(0.f, 0.f);
         if (lane0_left) r.pxl = ld(pp, d - 8);
         return r;
+    };
+    auto landed = [&](const InnerRow& r) {       // 0 once every load of r has arrived, see op_inner
+        return (int)((__float_as_uint(r.u.x) | __float_as_uint(r.ca.x) | __float_as_uint(r.cb.x) |
+                      __float_as_uint(r.px.x) | __float_as_uint(r.py.x)) & (TEEFLOW_LOAD_DEP ? P.zero_mask : 0u));
+    };
+    auto prefetch_row = [&](int rows_ahead) {    // into L2, see op_inner
+        const int d = rows_ahead * ROWB;
+        prefetch_l2(pu + d); prefetch_l2(pc + d); prefetch_l2(pc + d + PB); prefetch_l2(pp + d); prefetch_l2(pp + d + 2 * PB);
     };
     auto diff_x = [&](float2 v) {                // forward x-difference (zero in the last image column)
         const float2 d = sub2(make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1)), v);
@@ -666,7 +718,8 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
     for (int r = ra; r <= y1 + 1; ++r) {
         const bool has_a = r <= re;                            // row r exists (warp-uniform)
         const InnerRow row = nxt;
-        if (r < re) nxt = load_row(1);                         // row r + 1 is in flight while this step computes
+        if (r < re) nxt = load_row(1, landed(row));            // row r + 1 is in flight while this step computes
+        if (kPF > 0 && r + kPF <= re) prefetch_row(kPF);
         float2 u1 = zero2;
         if (has_a) {
             // A(r): estimateV + divergence(p) + estimateU, first iteration
@@ -740,7 +793,7 @@ __device__ __forceinline__ void op_wase(const EngineParams& P, int ucur, int slo
     if (x < g.W) {
         for (int y = y0; y < y1; ++y) {
             const unsigned q = (unsigned)(y * g.W + x);
-            const float2 u = SB[L::at(PL_U + (unsigned)ucur, y, x)];
+            const float2 u = __ldcg(SB + L::at(PL_U + (unsigned)ucur, y, x));
             const float2 w = __ldg(Wt + q);
             if (u.x != 0.f) { sum += (double)w.x * (double)u.x; cnt += (double)w.x; }
             if (u.y != 0.f) { sum += (double)w.y * (double)u.y; cnt += (double)w.y; }
@@ -768,7 +821,7 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
     if (x >= g.W) return;
     for (int y = y0; y < y1; ++y) {
         const unsigned q = (unsigned)(y * g.W + x);
-        float2 u = SB[L::at(PL_U + (unsigned)ucur, y, x)];
+        float2 u = __ldcg(SB + L::at(PL_U + (unsigned)ucur, y, x));
         u.x = (u.x - bg) * P.out_scale;
         u.y = (u.y - bg) * P.out_scale;
         if (P.flow_f32) {
@@ -784,10 +837,19 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
 }
 
 // ------------------------------------------------------------------------------------------- strip dispatch
-// Loads of the slot planes are PLAIN loads (never ld.global.nc): in the dataflow kernel a plane is rewritten by other
-// SMs between two reads of the same launch, and only ordinary loads are covered by the acquire fence a warp executes
-// after it has been handed a strip (the fence also drops the SM's stale L1 lines).  Read-only inputs (pyramid, WASE
-// weights, cubic table) keep the non-coherent path.
+// How the strip ops read the slot planes (the dataflow kernel re-reads, within ONE launch, planes that other SMs
+// rewrote in the meantime, so the non-coherent ld.global.nc path is never used for them):
+//   * streaming ops (inner, two-iteration pass, warp's flow row, WASE, final): every value is read once, with
+//     ld.global.cg -- served by L2, the point of coherence, so no stale L1 line can be hit;
+//   * ops that re-read neighbours through L1 (median: five taps per row; level-init: the four bilinear taps) use
+//     plain loads, and the warp executes an acquire fence (which also drops the SM's L1 lines) after it was handed
+//     the strip -- needs_l1_acquire().
+// Read-only inputs (pyramid, WASE weights) keep ld.global.nc.
+__device__ __forceinline__ bool needs_l1_acquire(int phase) { return phase == PH_MEDIAN || phase == PH_LEVEL_INIT; }
+
+#ifndef TEEFLOW_FLOW_STATS
+#define TEEFLOW_FLOW_STATS 0
+#endif
 #ifndef TEEFLOW_PHASE_MASK
 #define TEEFLOW_PHASE_MASK 0xffu
 #endif
@@ -972,17 +1034,35 @@ __device__ __forceinline__ void publish_task(const EngineParams& P, int slot, co
     const unsigned long long old = atomicAdd(&P.flow->alloc, (1ull << 32) | (unsigned long long)n_items);
     const unsigned k = (unsigned)(old >> 32), first = (unsigned)old;
     Task* t = P.tasks + (k & (kTaskRing - 1u));
-    uint4 hi;
-    hi.x = (unsigned)slot;
-    hi.y = (unsigned)phase | ((unsigned)n.level << 8) | ((unsigned)n.ucur << 16) | ((unsigned)n.pcur << 17);
-    hi.z = __float_as_uint(n.bg);
-    hi.w = 0u;
-    *reinterpret_cast<uint4*>(&t->slot) = hi;
-    __threadfence();                                   // the second half and everything the task reads is visible first
-    st_volatile_v4(t, make_uint4(k + 1u, first, n_items, (unsigned)n.pair));
+    const unsigned what = (phase == PH_EXIT ? 0u : n_items) | ((unsigned)phase << 20) | ((unsigned)n.level << 24) |
+                          ((unsigned)n.ucur << 28) | ((unsigned)n.pcur << 29);
+    const unsigned who = (unsigned)slot | ((unsigned)(n.pair < 0 ? 0 : n.pair) << 9);
+    __threadfence();                                   // everything the task reads is visible before its descriptor
+    st_volatile_v4(t, make_uint4(k + 1u, first, what, who));
 }
 
 constexpr unsigned kExitItems = 0x40000000u;   // ticket range of the terminal task: every warp takes one more ticket
+
+// lane 0 of the warp that retired the last strip of a task: advance the slot and hand its next task over
+__device__ __forceinline__ void retire_task(const EngineParams& P, int slot, double e, double e2) {
+    FlowCtl* const F = P.flow;
+    Slot& n = P.slots[0][slot];                        // only the warp that retires a slot's task touches its state
+    const int finished = next_state(P, n, e, e2, &F->next_pair);
+    P.arrive[slot] = 0u;
+    bool all_done = false;
+    if (finished >= 0) {
+        __threadfence();                               // the flow of the finished pair is visible before its index
+        const int pos = atomicAdd(&F->pairs_done, 1);
+        P.done_order[pos] = finished;
+        if (P.host_done) {                             // the host copies finished flows out while the rest is solved
+            __threadfence_system();
+            P.host_done[pos] = finished;
+        }
+        all_done = (pos + 1 == P.n_pairs);
+    }
+    if (n.phase != PH_IDLE) publish_task(P, slot, n, n.phase, (unsigned)items_of(P, n.phase, n.pair, n.level));
+    if (all_done) publish_task(P, slot, n, PH_EXIT, kExitItems);   // swallows every further ticket
+}
 
 template <int PITCH>
 __global__ void __launch_bounds__(kThreads, TEEFLOW_MIN_CTAS)
@@ -993,33 +1073,63 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
     __syncthreads();
     FlowCtl* const F = P.flow;
     unsigned kc = 0;                                   // task cursor of this warp: only ever moves forward
+#if TEEFLOW_FLOW_STATS
+    // diagnostic build: where do the warps spend their cycles?  [phase] strip time, [9] waiting for an unpublished
+    // task, [10] everything else (ticket, descriptor probe, fences, arrival, task hand-over); counts in [16 + i]
+    unsigned long long acc[11] = {0}, cnt[11] = {0};
+    long long c_prev = clock64();
+#define TF_STAT(i) { const long long c_now = clock64(); acc[i] += (unsigned long long)(c_now - c_prev); cnt[i] += 1; c_prev = c_now; }
+#define TF_STAT_FLUSH() { if (lane == 0) for (int i = 0; i < 11; ++i) { atomicAdd(P.flow_stats + i, acc[i]); atomicAdd(P.flow_stats + 16 + i, cnt[i]); } }
+#else
+#define TF_STAT(i)
+#define TF_STAT_FLUSH()
+#endif
+
+    // The scheduling round trips of a strip overlap each other instead of queueing up behind one another: the next
+    // ticket is requested BEFORE the release fence of the strip just finished (the fence drains the strip's stores
+    // while the ticket travels), and the arrival ticket is only looked at after the first descriptor probe of the
+    // next strip.  `pend_*` describe the strip whose arrival is still in flight (lane 0 holds its arrival ticket).
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(&F->ticket, 1u);
+    unsigned pend_arrive = 0, pend_n = 0;              // pend_n == 0: nothing pending
+    int pend_slot = 0, pend_phase = 0;
 
     for (;;) {
-        unsigned t = 0;
-        if (lane == 0) t = atomicAdd(&F->ticket, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
         // ---- which task owns ticket t?  32 descriptors per probe, one per lane
-        unsigned strip = 0, n_items = 0;
-        int pair = 0;
-        for (;;) {
+        uint4 desc = make_uint4(0u, 0u, 0u, 0u);
+        for (bool first_probe = true;; first_probe = false) {
             const Task* q = P.tasks + ((kc + (unsigned)lane) & (kTaskRing - 1u));
-            const uint4 d = ld_volatile_v4(q);         // seq, first, n_items, pair: one 16-byte store of the publisher
+            const uint4 d = ld_volatile_v4(q);         // the whole descriptor: one 16-byte store of the publisher
             const unsigned want = kc + (unsigned)lane + 1u;
             const bool pub = d.x == want;
-            const unsigned hit = __ballot_sync(0xffffffffu, pub && (t - d.y) < d.z);
+            const bool mine = pub && (((d.z >> 20) & 0xfu) == (unsigned)PH_EXIT || (t - d.y) < (d.z & kTaskItemsMax));
+            const unsigned hit = __ballot_sync(0xffffffffu, mine);
+            const unsigned unp = __ballot_sync(0xffffffffu, !pub);
+            const bool lost = __any_sync(0xffffffffu, (int)(d.x - want) > 0);
+            if (first_probe && pend_n) {
+                // the arrival of the previous strip has landed meanwhile: was it the last one of its task?
+                const bool last = __shfl_sync(0xffffffffu, (int)(pend_arrive == pend_n - 1u), 0) != 0;
+                if (last) {
+                    __threadfence();
+                    double e, e2;
+                    reduce_partials(P, pend_phase, pend_slot, (int)pend_n, lane, e, e2);
+                    if (lane == 0) retire_task(P, pend_slot, e, e2);
+                }
+                pend_n = 0;
+            }
             if (hit) {
                 const int src = __ffs(hit) - 1;
                 kc += (unsigned)src;
-                strip = t - __shfl_sync(0xffffffffu, d.y, src);
-                n_items = __shfl_sync(0xffffffffu, d.z, src);
-                pair = (int)__shfl_sync(0xffffffffu, d.w, src);
+                desc.x = __shfl_sync(0xffffffffu, d.x, src); desc.y = __shfl_sync(0xffffffffu, d.y, src);
+                desc.z = __shfl_sync(0xffffffffu, d.z, src); desc.w = __shfl_sync(0xffffffffu, d.w, src);
                 break;
             }
             // a descriptor of a later lap of the ring: this warp lagged kTaskRing tasks behind (cannot happen in practice)
-            if (__any_sync(0xffffffffu, (int)(d.x - want) > 0)) { if (lane == 0) atomicExch(&F->abort, 2); return; }
-            const unsigned unp = __ballot_sync(0xffffffffu, !pub);
+            if (lost) { if (lane == 0) atomicExch(&F->abort, 2); TF_STAT_FLUSH() return; }
             if (unp == 0u) { kc += 32u; continue; }    // 32 published tasks, all of them before ticket t
             kc += (unsigned)(__ffs(unp) - 1);          // the first unpublished one: wait until it appears (one lane polls)
+            TF_STAT(10)
             int give_up = 0;
             if (lane == 0) {
                 const unsigned* seq = &P.tasks[kc & (kTaskRing - 1u)].seq;
@@ -1032,42 +1142,34 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
                     if (ns < 2048) ns *= 2;
                 }
             }
-            if (__shfl_sync(0xffffffffu, give_up, 0)) return;
+            TF_STAT(9)
+            if (__shfl_sync(0xffffffffu, give_up, 0)) { TF_STAT_FLUSH() return; }
         }
-        __threadfence();                               // acquire: what the task's publisher (and its strips) wrote
-        const Task* tk = P.tasks + (kc & (kTaskRing - 1u));
-        const uint4 hi = __ldcg(reinterpret_cast<const uint4*>(&tk->slot));
-        const int slot = (int)hi.x;
-        const int phase = (int)(hi.y & 0xffu), level = (int)((hi.y >> 8) & 0xffu);
-        const int ucur = (int)((hi.y >> 16) & 1u), pcur = (int)((hi.y >> 17) & 1u);
-        if (phase == PH_EXIT) return;
+        const int phase = (int)((desc.z >> 20) & 0xfu);
+        if (phase == PH_EXIT) { TF_STAT(10) TF_STAT_FLUSH() return; }
+        const unsigned n_items = desc.z & kTaskItemsMax;
+        const int level = (int)((desc.z >> 24) & 0xfu), ucur = (int)((desc.z >> 28) & 1u), pcur = (int)((desc.z >> 29) & 1u);
+        const int slot = (int)(desc.w & 0x1ffu), pair = (int)(desc.w >> 9);
+        const int strip = (int)(t - desc.y);
+        if (needs_l1_acquire(phase)) __threadfence();  // plain (L1) plane reads ahead: drop the SM's stale lines
+        const float bg = (phase == PH_FINAL && P.wase_w) ? __ldcg(P.bg_out + pair) : 0.f;
+        TF_STAT(10)
 
         double err = 0.0, aux = 0.0;
-        run_strip<PITCH>(P, phase, level, ucur, pcur, pair, __uint_as_float(hi.z), slot, (int)strip, lane, s_cubic, err, aux);
+        run_strip<PITCH>(P, phase, level, ucur, pcur, pair, bg, slot, strip, lane, s_cubic, err, aux);
         __syncwarp();
-        if (strip_arrive(P, phase, slot, (int)strip, (int)n_items, lane, err, aux)) {
-            __threadfence();
-            double e, e2;
-            reduce_partials(P, phase, slot, (int)n_items, lane, e, e2);
-            if (lane == 0) {
-                Slot& n = P.slots[0][slot];            // only the warp that retires a slot's task touches its state
-                const int finished = next_state(P, n, e, e2, &F->next_pair);
-                P.arrive[slot] = 0u;
-                bool all_done = false;
-                if (finished >= 0) {
-                    __threadfence();                   // the flow of the finished pair is visible before its index
-                    const int pos = atomicAdd(&F->pairs_done, 1);
-                    P.done_order[pos] = finished;
-                    if (P.host_done) {                 // the host copies finished flows out while the rest is solved
-                        __threadfence_system();
-                        P.host_done[pos] = finished;
-                    }
-                    all_done = (pos + 1 == P.n_pairs);
-                }
-                if (n.phase != PH_IDLE) publish_task(P, slot, n, n.phase, (unsigned)items_of(P, n.phase, n.pair, n.level));
-                if (all_done) publish_task(P, slot, n, PH_EXIT, kExitItems);   // swallows every further ticket
+        TF_STAT(phase)
+        if (lane == 0) {
+            if (phase == PH_INNER) P.partial[(size_t)slot * P.max_tiles + strip] = err;
+            if (phase == PH_WASE || phase == PH_INNER2) {
+                P.partial[(size_t)slot * P.max_tiles + 2 * strip] = err;
+                P.partial[(size_t)slot * P.max_tiles + 2 * strip + 1] = aux;
             }
+            t = atomicAdd(&F->ticket, 1u);             // travels while the fence below drains this strip's stores
+            __threadfence();
+            pend_arrive = atomicAdd(P.arrive + slot, 1u);
         }
+        pend_n = n_items; pend_slot = slot; pend_phase = phase;
     }
 }
 

@@ -391,6 +391,12 @@ class TVL1Engine:
         info = {k: getattr(st, k) for k, _ in _lib.TeeflowStats._fields_ if k != "reserved"}
         return buf[:n, :st.n_levels].copy(), info
 
+    def flow_stats(self):
+        """Diagnostic builds (-DTEEFLOW_FLOW_STATS=1): (enabled, cycles[16], counts[16]) of the last dataflow run."""
+        buf = (C.c_uint64 * 32)()
+        on = self._check(self._lib.teeflow_get_flow_stats(self._h, buf))
+        return bool(on), np.array(buf[:16], np.float64), np.array(buf[16:], np.float64)
+
     def time_launches(self, n: int) -> None:
         """Diagnostics: time the first n solver launches of every following calc (teeflow_time_launches)."""
         self._check(self._lib.teeflow_time_launches(self._h, int(n)))

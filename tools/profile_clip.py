@@ -15,3 +15,11 @@ for r in range(reps):
     torch.cuda.synchronize()
     c, info = eng.last_counters()
     print(r, info, "pairs/s", (n - 1) / info["device_ms"] * 1e3, flush=True)
+on, cyc, cnt = eng.flow_stats()
+if on:
+    names = {1: "level_init", 2: "warp", 3: "median", 4: "inner", 5: "final", 6: "wase", 7: "inner2", 9: "wait", 10: "sched"}
+    tot = cyc.sum()
+    print("flow stats (share of warp cycles, intervals, mean cycles):")
+    for i, nme in names.items():
+        if cnt[i]:
+            print(f"  {nme:10s} {100 * cyc[i] / tot:6.2f} %  n={int(cnt[i]):9d}  mean={cyc[i] / cnt[i]:10.0f}")
