@@ -1,19 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- TV-L1 frame-pairs/s at 600x800 (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode weak|strong]
 
 A "step" is one pass of the hot path over one synthetic 64-frame 600x800 uint8 clip (BASELINE.json configs[1]):
 63 frame pairs, TV-L1 defaults (lambda 0.15, 5 scales, 5 warps, early exit active), all pairs in flight.
   value   : frame-pairs/s, clip already resident in HBM (device-pointer C ABI: teeflow_calc_clip).
   e2e     : the same through the host-buffer entry point (teeflow_calc_clip_host): H2D of the uint8 clip from
-            pinned memory and D2H of the fp16 flow (the reference's stored result) inside the timed region.
-  roofline: algorithmic bytes of the solver kernel (SURVEY.md §8d, from the iteration counters the engine
-            returns) / its device time, against the measured HBM copy bandwidth.
+            pinned memory and D2H of the fp16 flow (the reference's stored result) inside the timed region; next to
+            it the route a user of the Python mirror takes, TVL1Engine.calc_clip(numpy array) on pageable memory.
+  roofline: algorithmic bytes of the solver kernel (SURVEY.md 8d, from the iteration counters the engine
+            returns) / its device time (CUDA events around the one dataflow launch), against the measured HBM copy
+            bandwidth.
+  gates   : (N = 1) correctness next to the number: mean EPE / max |d| of all 63 pairs against the CPU oracle with
+            OpenCV's serial float32 error sum, and whether the downstream systole / diastole and e' / l' / a' frame
+            indices (reference defaults) equal those of the oracle chain.
   cpu_baseline / --impl reference: the CPU port of OpenCV's DualTVL1 (oracle/, the only CPU implementation of
-            the path that can run here -- cv2.optflow is not installable) on the host cores.
-N > 1 (torchrun): every rank solves its own clip (frame pairs are independent; weak scaling), no data-path
-collective; time is the max over ranks.
+            the path that can run here -- cv2.optflow is not installable) on the host cores: 8 pairs spread over the
+            clip, median of 3, all cores and one thread.
+N > 1 (torchrun), --mode weak (default): rank r solves its own clip (seed r: TV-L1 cost is data dependent, so the
+ranks' times differ; per-rank times and the imbalance are reported), no data-path collective, time = max over ranks.
+--mode strong: a fixed batch of clips is split over the ranks by the reference's nchunks rule
+(calculate_optical_flow.py:266-269) or round robin, every rank runs its share through one scheduler run, and the
+per-frame waveform rows are all-gathered over NCCL -- the only exchange of the path.
 """
 from __future__ import annotations
 
@@ -101,21 +110,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_rate(frames: np.ndarray, n_pairs: int, repeats: int = 1):
-    """Times the CPU port of OpenCV's DualTVL1 (faithful serial-float32 error sum) on `n_pairs` pairs."""
+WORKLOAD = ("synthetic 64-frame 600x800 uint8 clip per GPU, TV-L1 defaults (lambda 0.15, 5 scales, 5 warps, inner 30 x "
+            "outer 10 with early exit, median 5), 63 frame pairs in flight, fp16 flow (N,H,W,2) out")
+SAMPLE_PAIRS = [0, 8, 16, 24, 32, 40, 48, 56]      # >= 8 pairs, spread over the clip
+
+
+def cpu_reference_rate(frames: np.ndarray, pairs, threads: int = 0, repeats: int = 1):
+    """Times the CPU port of OpenCV's DualTVL1 (faithful serial-float32 error sum) on the given pair indices.
+    Returns (median pairs/s over `repeats`, threads used, kind, implementation name)."""
     from oracle import tvl1_oracle as O
     O.build()
     model, kind_name = O.create_reference_model()
-    cores = O.set_threads(0)          # all host cores (torchrun exports OMP_NUM_THREADS=1)
-    best = None
+    cores = O.set_threads(threads)    # 0 = all host cores (torchrun exports OMP_NUM_THREADS=1)
+    rates = []
     for _ in range(repeats):
         t = time.perf_counter()
-        for i in range(n_pairs):
+        for i in pairs:
             model.calc(frames[i], frames[i + 1], None)
-        dt = time.perf_counter() - t
-        best = dt if best is None else min(best, dt)
+        rates.append(len(pairs) / (time.perf_counter() - t))
     kind = "reference" if kind_name == "cv2.optflow" else "port"
-    return n_pairs / best, cores, kind, kind_name
+    return float(np.median(rates)), cores, kind, kind_name
 
 
 def run_reference_arm(args):
@@ -123,31 +137,81 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     from tee_optical_flow_b200.synth import make_clip
-    sample_pairs = 2
-    frames = make_clip(seed=0, n_frames=sample_pairs + 1, H=H, W=W)
-    for _ in range(args.warmup):
-        cpu_reference_rate(frames, 1)
+    frames = make_clip(seed=0, n_frames=N_FRAMES, H=H, W=W)
+    for _ in range(min(args.warmup, 2)):
+        cpu_reference_rate(frames, SAMPLE_PAIRS[:2])
     t0 = time.perf_counter()
-    rates = []
+    cores = kind = kind_name = None
     for _ in range(args.steps):
-        r, cores, kind, kind_name = cpu_reference_rate(frames, sample_pairs)
-        rates.append(r)
+        _, cores, kind, kind_name = cpu_reference_rate(frames, SAMPLE_PAIRS)
     total = time.perf_counter() - t0
-    value = sample_pairs * args.steps / total
+    value = len(SAMPLE_PAIRS) * args.steps / total
+    one, _, _, _ = cpu_reference_rate(frames, SAMPLE_PAIRS[:4], threads=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic 64-frame 600x800 uint8 clip, TV-L1 defaults (lambda 0.15, 5 scales, 5 warps)",
-                   "sample": f"first {sample_pairs} frame pairs of the clip per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                         "sample": f"{sample_pairs} frame pairs x {args.steps} steps of the same 600x800 clip "
-                                   f"({kind_name}; OpenMP on all host cores, serial float32 error sum like OpenCV)"},
+        "config": {"workload": WORKLOAD,
+                   "sample": f"{len(SAMPLE_PAIRS)} frame pairs spread over the clip (indices {SAMPLE_PAIRS}) per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "one_thread_value": one,
+                         "sample": f"{len(SAMPLE_PAIRS)} frame pairs spread over the same 600x800 clip x {args.steps} steps "
+                                   f"({kind_name}; OpenMP on all host cores, serial float32 error sum like OpenCV); "
+                                   f"one_thread_value: 4 of those pairs on 1 thread"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def correctness_gates(eng, frames_np, device):
+    """BASELINE.md 3.5 / SURVEY.md 8d: the gates that go with the number.  Runs the CPU oracle (OpenCV-faithful serial
+    float32 error sum) on all pairs of the benchmark clip and the reference's downstream chain (restated in oracle/)
+    on its fp16 flow; compares with the engine's flow and with the engine chain (GPU reductions + waveforms.py)."""
+    import torch
+    from oracle import downstream_ref as R
+    from oracle import tvl1_oracle as O
+    from tee_optical_flow_b200 import waveforms as Wv
+    from tee_optical_flow_b200.masks import calc_AV_centroid
+    from tee_optical_flow_b200.synth import make_clip, make_masks
+    O.build()
+    O.set_threads(0)
+    om = O.OracleDualTVL1(err_mode=0)
+    n = frames_np.shape[0]
+    t = time.perf_counter()
+    ref = np.stack([om.calc(frames_np[i], frames_np[i + 1]) for i in range(n - 1)])
+    oracle_s = time.perf_counter() - t
+    f32, _ = eng.calc_clip(torch.from_numpy(frames_np).to(device), duplicate_last=False)
+    got = f32.cpu().numpy()
+    epe = np.sqrt(((got.astype(np.float64) - ref) ** 2).sum(-1))
+    # downstream gate on a second clip of the same size whose motion period (24 frames) gives the reference's pickers
+    # complete cardiac cycles: on the benchmark clip (period 32) the last systole run leaves a 2-frame tail gap, on
+    # which the reference's own e' / l' / a' windows are empty and its code raises (both chains agree on that too)
+    H_, W_ = frames_np.shape[1:]
+    cyc = make_clip(seed=0, n_frames=n, H=H_, W=W_, period=24.0)
+    masks = make_masks(0, n, H_, W_, period=24.0)
+    nframes = n - 2
+    cf = np.float32(0.05 * 40.0)
+    ref_c = np.stack([om.calc(cyc[i], cyc[i + 1]) for i in range(n - 1)])
+    ref16 = (np.concatenate([ref_c, ref_c[-1:]]) * cf).astype(np.float16)
+    _, got16 = eng.calc_clip(torch.from_numpy(cyc).to(device), out_scale=float(cf), duplicate_last=True, want_f32=False, want_f16=True)
+    want = R.clip_indices(ref16, masks["rv"], masks["av"], nframes)
+    cent = np.asarray(calc_AV_centroid(eng, masks["av"], nframes, filter=True))
+    res = eng.analyze_clip(got16, masks["rv"], cent, nframes, 1, 99)
+    mine = Wv.indices_of(Wv.clip_waveform_indices(res, nframes, frame_rate=40.0, strict=False))
+    keys = ("sys_frames", "dia_frames", "single", "radial", "longitudinal")
+    return {
+        "mean_epe": float(epe.mean()), "max_abs": float(np.abs(got - ref).max()),
+        "worst_pair_mean_epe": float(epe.reshape(n - 1, -1).mean(1).max()), "pairs": n - 1,
+        "bit_identical_pairs": int(sum(np.array_equal(got[i], ref[i]) for i in range(n - 1))),
+        "indices_equal": bool(all(mine[k] == want[k] for k in keys)),
+        "indices": {"sys_frames": mine["sys_frames"], "single": mine["single"], "radial": mine["radial"]},
+        "indices_clip": "synthetic 64-frame 600x800 clip, seed 0, motion period 24 frames, RVIO_2class masks, x2.0 cm/s",
+        "tolerance": "mean EPE <= 1e-2 px (north_star); indices bit-exact",
+        "oracle": "oracle/tvl1_oracle.c, serial float32 error sum like OpenCV (parity of the oracle itself: unpinned, "
+                  "DESIGN.md); downstream: oracle/downstream_ref.py, reference default configs",
+        "oracle_seconds": oracle_s,
+    }
 
 
 def phase_probe(frames_dev, device):
@@ -185,6 +249,69 @@ def phase_probe(frames_dev, device):
     return out
 
 
+def strong_scaling(args, eng, dev, world, rank):
+    """BASELINE config 4 in miniature: a FIXED batch of clips split over the ranks, every rank's share through one
+    scheduler run (slots freed by one clip are refilled from the next), then the all-gather of the per-frame
+    waveform rows.  Assignment: 'contiguous' = the reference's nchunks rule (rank r == chunk r), 'roundrobin'."""
+    import torch
+    import torch.distributed as dist
+    from tee_optical_flow_b200.sharding import chunk_bounds, gather_rows
+    from tee_optical_flow_b200.synth import make_clip
+    B, nf = args.batch, args.batch_frames
+    if args.assign == "contiguous":
+        lo, hi = chunk_bounds(B, world, rank)
+        mine = list(range(lo, hi))
+    else:
+        mine = list(range(rank, B - B % world, world))
+    clips = np.stack([make_clip(seed=c, n_frames=nf, H=H, W=W) for c in mine])
+    d = torch.from_numpy(clips).to(dev)
+    out16 = None
+
+    def step():
+        nonlocal out16
+        _, out16 = eng.calc_batch(d, want_f32=False, want_f16=True)
+        counters, _ = eng.last_counters()
+        rows = counters[:, :, 0].sum(axis=1, keepdims=True).astype(np.float64)       # inner iterations per pair
+        if world > 1:                                                               # every rank: len(mine) * (nf-1) rows
+            buf = torch.from_numpy(rows).to(dev)
+            allr = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device=dev)
+            dist.all_gather_into_tensor(allr, buf)
+        return rows
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        rows = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    mine_s = ev0.elapsed_time(ev1) / 1e3
+    t = torch.tensor([mine_s], dtype=torch.float64, device=dev)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(allt, t)
+    else:
+        allt = [t]
+    per_rank = [float(x.item()) for x in allt]
+    if rank == 0:
+        pairs = (B - B % world) * (nf - 1)
+        line = {"metric": METRIC, "value": pairs * args.steps / max(per_rank), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * max(per_rank) / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"fixed batch of {B} synthetic {nf}-frame 600x800 uint8 clips (seeds 0..{B - 1}) split over "
+                                       f"the ranks ({args.assign}; the reference's nchunks rule drops the remainder), TV-L1 "
+                                       "defaults, fp16 flow out, all-gather of per-pair rows",
+                           "clips_per_rank": len(mine), "pairs_total": pairs},
+                "per_rank_ms_per_step": [1e3 * x / args.steps for x in per_rank],
+                "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / len(per_rank)),
+                "inner_iterations_per_pair_rank0": float(rows.mean())}
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,7 +319,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="teeflow", choices=["teeflow", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gates", action="store_true")
     ap.add_argument("--slots", type=int, default=0)
+    ap.add_argument("--mode", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=16, help="--mode strong: clips in the fixed batch")
+    ap.add_argument("--batch-frames", type=int, default=16, help="--mode strong: frames per clip")
+    ap.add_argument("--assign", default="contiguous", choices=["contiguous", "roundrobin"])
+    ap.add_argument("--same-seed", action="store_true", help="weak mode: every rank solves the seed-0 clip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "teeflow" else args.warmup
 
@@ -214,14 +347,20 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    eng = TVL1Engine(device=local_rank, max_slots=args.slots)
+    if args.mode == "strong":
+        strong_scaling(args, eng, dev, world, rank)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
-    # every rank solves its own copy of the SAME synthetic clip (seed 0): TV-L1 cost is data dependent (early exit:
-    # 70-91 ms per clip over seeds 0..7, tools/seed_times.py), so identical clips keep the per-GPU work fixed as N
-    # grows -- a clean weak-scaling measurement.  Frame pairs are independent units, no data-path collective.
-    frames_np = make_clip(seed=0, n_frames=N_FRAMES, H=H, W=W)
+    # weak scaling: rank r solves its own clip, seed r (rank 0 / N = 1: the seed-0 clip of BASELINE configs[1]).  TV-L1 cost
+    # is data dependent (early exit), so the ranks finish at different times: that imbalance, not a collective, is what
+    # limits 1 -> N, and it is reported.  Frame pairs are independent units, no data-path collective.
+    seed = 0 if args.same_seed else rank
+    frames_np = make_clip(seed=seed, n_frames=N_FRAMES, H=H, W=W)
     frames_dev = torch.from_numpy(frames_np).to(dev)
     n_pairs = N_FRAMES - 1
-    eng = TVL1Engine(device=local_rank, max_slots=args.slots)
     out16 = torch.empty((N_FRAMES, H, W, 2), dtype=torch.float16, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -247,7 +386,7 @@ def main():
         step_device()
         _, info = eng.last_counters()
         solver_ms += info["solver_ms"]; pyr_ms += info["pyramid_ms"]
-        launches += info["solver_launches"]; kernel_launches += info["kernel_launches"]
+        launches += info["solver_launches"]; kernel_launches += info["kernel_launches"] + 1    # + the L2-flush fill
     ev1.record()
     barrier()
     wall_s = time.perf_counter() - t_wall
@@ -276,6 +415,19 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
+
+    # ---- the same through the Python mirror a reference user calls: TVL1Engine.calc_clip(numpy array), pageable memory
+    def step_pageable():
+        flush.fill_(1)
+        return eng.calc_clip(frames_np, want_f32=False, want_f16=True)
+
+    step_pageable()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(args.steps // 2, 1)):
+        step_pageable()
+    barrier()
+    pageable_s = (time.perf_counter() - t0) / max(args.steps // 2, 1)
 
     # ---- BASELINE config 3 (informational, outside the headline metric): masked radial / longitudinal
     # decomposition + exact per-frame percentiles / angle mode of the stored fp16 flow, then (N > 1) the NCCL
@@ -313,9 +465,9 @@ def main():
     except Exception as e:  # informational only
         analysis = {"error": str(e)[:200]}
 
-    # ---- per-phase roofline (rank 0, informational): the step kernel runs four different strip ops; with one slot
-    # group and ONE pyramid level all 63 pairs step in lockstep at first, so launch 0 is a pure level-init, 1 a pure
-    # warp, 2 a pure median and 3.. pure inner iterations over 63 x 600 x 800 px -- timed with CUDA events per launch
+    # ---- per-phase roofline (rank 0, informational): the stepped scheduler with one slot group and ONE pyramid level
+    # steps all 63 pairs in lockstep at first, so launch 0 is a pure level-init, 1 a pure warp, 2 a pure median and 3..
+    # pure inner iterations over 63 x 600 x 800 px -- timed with CUDA events per launch
     phases = None
     if rank == 0:
         try:
@@ -323,10 +475,14 @@ def main():
         except Exception as e:  # informational only
             phases = {"error": str(e)[:200]}
 
-    t_max = torch.tensor([dev_s, wall_s, e2e_s], dtype=torch.float64, device=dev)
+    mine = torch.tensor([dev_s, wall_s, e2e_s, pageable_s], dtype=torch.float64, device=dev)
+    allv = [torch.zeros_like(mine) for _ in range(world)]
     if world > 1:
-        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
-    dev_s, wall_s, e2e_s = [float(x) for x in t_max.tolist()]
+        dist.all_gather(allv, mine)
+    else:
+        allv = [mine]
+    per_rank = np.stack([x.cpu().numpy() for x in allv])             # [rank][dev, wall, e2e, pageable]
+    dev_s, wall_s, e2e_s, pageable_s = [float(x) for x in per_rank.max(axis=0)]
     step_s = max(dev_s, 1e-9)
 
     if rank == 0:
@@ -348,10 +504,10 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * step_s / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": "synthetic 64-frame 600x800 uint8 clip per GPU, TV-L1 defaults (lambda 0.15, 5 scales, "
-                            "5 warps, inner 30 x outer 10 with early exit, median 5), 63 frame pairs in flight, "
-                            "fp16 flow (N,H,W,2) out",
+                "workload": WORKLOAD,
                 "pairs_per_step_per_gpu": n_pairs, "slots": info["n_slots"],
+                "seeds": "rank r solves the clip of seed r (rank 0: seed 0)" if not args.same_seed else "seed 0 on every rank",
+                "scheduler": "dataflow: one cooperative launch per clip" if info["solver_launches"] == 1 else "stepped",
                 "l2": "256 MiB buffer written between steps (L2 flush, inside the timed region); solver state "
                       "3.4 GB >> 126 MB L2",
                 "inner_iterations_per_pair_mean": float(counters[:, :, 0].sum() / n_pairs),
@@ -360,10 +516,15 @@ def main():
             "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "kernel_time_fraction": (solver_ms + pyr_ms) / 1e3 / max(wall_s, 1e-9),
             "gpu_launches": int(kernel_launches),
+            "per_rank_ms_per_step": [1e3 * float(x) / args.steps for x in per_rank[:, 0]],
+            "imbalance_max_over_mean": float(per_rank[:, 0].max() / per_rank[:, 0].mean()),
             "e2e": {"value": world * n_pairs * args.steps / e2e_s, "unit": UNIT,
                     "h2d_bytes_per_step": int(frames_np.nbytes), "d2h_bytes_per_step": int(out_np.nbytes),
-                    "api": "teeflow_calc_clip_host (pinned host buffers)"},
-            "roofline": {"bound": "hbm", "kernel": "tvl1_step_kernel", "achieved": achieved, "peak": peak,
+                    "api": "teeflow_calc_clip_host (pinned host buffers)",
+                    "pageable_value": world * n_pairs / pageable_s,
+                    "pageable_api": "TVL1Engine.calc_clip(numpy array): pageable memory, output arrays allocated per call"},
+            "roofline": {"bound": "hbm", "kernel": "tvl1_flow_kernel" if info["solver_launches"] == 1 else "tvl1_step_kernel",
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_launch_ms,
                          "launches_per_step": launches / args.steps,
@@ -373,11 +534,17 @@ def main():
             "phase_roofline": phases,
         }
         if world == 1 and not args.no_cpu_baseline:
-            sample_pairs = 6
-            rate, cores, kind, kind_name = cpu_reference_rate(frames_np, sample_pairs)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": f"first {sample_pairs} frame pairs of the same 600x800 clip "
-                                              f"({kind_name}, OpenMP on all host cores)"}
+            rate, cores, kind, kind_name = cpu_reference_rate(frames_np, SAMPLE_PAIRS, repeats=3)
+            one, _, _, _ = cpu_reference_rate(frames_np, SAMPLE_PAIRS[:4], threads=1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "one_thread_value": one,
+                                    "sample": f"{len(SAMPLE_PAIRS)} frame pairs spread over the same 600x800 clip, median "
+                                              f"of 3 ({kind_name}, OpenMP on all host cores); one_thread_value: 4 of "
+                                              "those pairs on 1 thread"}
+            if not args.no_gates:
+                try:
+                    line["gates"] = correctness_gates(eng, frames_np, dev)
+                except Exception as e:
+                    line["gates"] = {"error": str(e)[:300]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -48,9 +48,6 @@ constexpr int kWarpPF = TEEFLOW_WARP_PF;   // warp op: tap rows pulled into L2 a
 #ifndef TEEFLOW_LATE_HANDOVER
 #define TEEFLOW_LATE_HANDOVER 1
 #endif
-#ifndef TEEFLOW_LOAD_DEP
-#define TEEFLOW_LOAD_DEP 0
-#endif
 #ifndef TEEFLOW_PF_ROWS
 #define TEEFLOW_PF_ROWS 4
 #endif
@@ -524,8 +521,8 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         else return const_cast<char*>(p) + dp;
     };
     auto st = [](char* p, int off, float2 v) { *reinterpret_cast<float2*>(p + off) = v; };
-    auto load_row = [&](int rows_ahead, int dep = 0) {
-        const int d = rows_ahead * ROWB + dep;
+    auto load_row = [&](int rows_ahead) {
+        const int d = rows_ahead * ROWB;
         InnerRow r;
         r.u = ld(pu, d);
         r.ca = ld(pc, d);
@@ -535,15 +532,6 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         r.pxl = make_float2(0.f, 0.f);
         if (lane0_left) r.pxl = ld(pp, d - 8);   // only lane 0 of a strip that does not start at x = 0
         return r;
-    };
-    // `landed(row)` is 0, computed from every load of `row` through a mask the compiler cannot see through.  Adding it
-    // to the addresses of the NEXT batch of loads makes that batch wait until this one has arrived.  Without it the
-    // hardware's counting scoreboards decide: when ptxas lets the new loads share a scoreboard with the previous
-    // batch, the first use of the previous batch waits for the NEW loads as well -- a whole DRAM round trip per row
-    // with nothing overlapped (ncu: one MUFU.RCP held 21 % of all stall samples of the run).
-    auto landed = [&](const InnerRow& r) {
-        return (int)((__float_as_uint(r.u.x) | __float_as_uint(r.ca.x) | __float_as_uint(r.cb.x) |
-                      __float_as_uint(r.px.x) | __float_as_uint(r.py.x)) & (TEEFLOW_LOAD_DEP ? P.zero_mask : 0u));
     };
     // The register look-ahead is one row (~1.5 us of work per warp); under load a DRAM access takes about as long, and
     // with the other phases' warps on the SM too few bytes are in flight (the first use of the next row's loads was
@@ -692,8 +680,8 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
 
     auto ld = [](const char* p, int off) { return __ldcg(reinterpret_cast<const float2*>(p + off)); };
     auto st = [](const char* p, int off, float2 v) { *reinterpret_cast<float2*>(const_cast<char*>(p) + off) = v; };
-    auto load_row = [&](int rows_ahead, int dep = 0) {
-        const int d = rows_ahead * ROWB + dep;
+    auto load_row = [&](int rows_ahead) {
+        const int d = rows_ahead * ROWB;
         InnerRow r;
         r.u = ld(pu, d);
         r.ca = ld(pc, d);
@@ -703,10 +691,6 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
         r.pxl = make_float2(0.f, 0.f);
         if (lane0_left) r.pxl = ld(pp, d - 8);
         return r;
-    };
-    auto landed = [&](const InnerRow& r) {       // 0 once every load of r has arrived, see op_inner
-        return (int)((__float_as_uint(r.u.x) | __float_as_uint(r.ca.x) | __float_as_uint(r.cb.x) |
-                      __float_as_uint(r.px.x) | __float_as_uint(r.py.x)) & (TEEFLOW_LOAD_DEP ? P.zero_mask : 0u));
     };
     auto prefetch_row = [&](int rows_ahead) {    // into L2, see op_inner
         const int d = rows_ahead * ROWB;
@@ -729,13 +713,13 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
     float2 u2p = zero2;                                       // u'' of row r-2 (when a step starts)
     float2 ca_p = zero2, cb_p = zero2, px_p = zero2;          // inputs of row r-1
     float2 py_p = ra >= 1 ? ld(pp, 2 * PB - ROWB) : zero2;
-    InnerRow nxt = load_row(0);                               // row ra
+    InnerRow row = load_row(0);                               // row ra
 
 #pragma unroll 1
     for (int r = ra; r <= y1 + 1; ++r) {
         const bool has_a = r <= re;                            // row r exists (warp-uniform)
-        const InnerRow row = nxt;
-        if (r < re) nxt = load_row(1, landed(row));            // row r + 1 is in flight while this step computes
+        InnerRow nxt = row;
+        if (r < re) nxt = load_row(1);                         // row r + 1 is in flight while this step computes
         if (kPF > 0 && r + kPF <= re) prefetch_row(kPF);
         float2 u1 = zero2;
         if (has_a) {
@@ -777,8 +761,18 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
             if (!dual_update_fast(ux, uy, p1x, p1y, K, pxn, pyn)) dual_update_exact(ux, uy, p1x, p1y, K, pxn, pyn);
             if (owner) { st(pp, dp - 2 * ROWB, pxn); st(pp, dp - 2 * ROWB + 2 * PB, pyn); }
         }
-        u1p = u1; p1x = n1x; p1y = n1y; u2p = u2;
         ca_p = row.ca; cb_p = row.cb; px_p = row.px; py_p = row.py;
+        row = nxt;                                             // first use of the loads: a whole row step after their issue
+#if TEEFLOW_LATE_HANDOVER
+        {   // see op_inner: keeps ptxas from hoisting the hand-over onto the loads
+            const unsigned late = (__float_as_uint(u2.x) | __float_as_uint(n1y.y)) & P.zero_mask;
+            row.px = make_float2(__uint_as_float(__float_as_uint(nxt.px.x) | late), __uint_as_float(__float_as_uint(nxt.px.y) | late));
+            row.py = make_float2(__uint_as_float(__float_as_uint(nxt.py.x) | late), __uint_as_float(__float_as_uint(nxt.py.y) | late));
+            row.ca = make_float2(__uint_as_float(__float_as_uint(nxt.ca.x) | late), __uint_as_float(__float_as_uint(nxt.ca.y) | late));
+            row.cb = make_float2(__uint_as_float(__float_as_uint(nxt.cb.x) | late), __uint_as_float(__float_as_uint(nxt.cb.y) | late));
+        }
+#endif
+        u1p = u1; p1x = n1x; p1y = n1y; u2p = u2;
         pu += ROWB; pp += ROWB; pc += ROWB;
     }
 #pragma unroll

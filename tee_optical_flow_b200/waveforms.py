@@ -263,29 +263,44 @@ def calculate_single_peaks(filt_arr, frame_times, sys_frames, dia_frames, nframe
 def clip_waveform_indices(analysis: Dict[str, np.ndarray], nframes: int, frame_rate: float = 1.0,
                           cc_config: Optional[CardiacCycleConfig] = None,
                           peak_config: Optional[PeakDetectionConfig] = None,
-                          single_smooth_fraction: float = 0.5) -> Dict[str, object]:
+                          single_smooth_fraction: float = 0.5, strict: bool = True) -> Dict[str, object]:
     """The reference's downstream order of operations (example_peak_plots.py:124-267) on the per-frame waveforms of
     one label, as TVL1Engine.analyze_clip returns them ('ang_mode', 'mag_hi', 'rad_hi', 'rad_lo', 'long_hi',
     'long_lo'): angle-based systole / diastole runs, then systolic / e' / l' / a' frame indices of the magnitude
-    curve and of the radial and longitudinal curve pairs.  Defaults = the reference's configs (config.py:13-16, 75-82)."""
+    curve and of the radial and longitudinal curve pairs.  Defaults = the reference's configs (config.py:13-16, 75-82).
+    The reference's pickers raise ValueError when a fallback window is empty (np.argmax of an empty slice,
+    peak_detection.py:56, 115-133); strict=True propagates that like the reference, strict=False records
+    {'raises': 'ValueError'} for that curve and goes on with the others."""
     cc = cc_config or CardiacCycleConfig()
     pk = peak_config or PeakDetectionConfig()
     frame_times = np.arange(nframes) * (1000.0 / frame_rate)
     sys_frames, dia_frames = angle_cycle_intervals(np.asarray(analysis['ang_mode'], dtype=np.float64)[:nframes], cc)
     out: Dict[str, object] = {'sys_frames': [[int(a), int(b)] for a, b in sys_frames],
                               'dia_frames': [[int(a), int(b)] for a, b in dia_frames]}
-    filt_mag = spectral_smooth(np.asarray(analysis['mag_hi'], dtype=np.float64)[:nframes], single_smooth_fraction, pk.pad_len)
-    out['single'] = calculate_single_peaks(filt_mag, frame_times, sys_frames, dia_frames, nframes, 'angle',
-                                           pk.peak_thres, pk.min_dist, pk.pick_peak_by_subset)
+
+    def stage(fn):
+        if strict:
+            return fn()
+        try:
+            return fn()
+        except ValueError:
+            return {'raises': 'ValueError'}
+
+    out['single'] = stage(lambda: calculate_single_peaks(
+        spectral_smooth(np.asarray(analysis['mag_hi'], dtype=np.float64)[:nframes], single_smooth_fraction, pk.pad_len),
+        frame_times, sys_frames, dia_frames, nframes, 'angle', pk.peak_thres, pk.min_dist, pk.pick_peak_by_subset))
     for name, hi, lo in (('radial', 'rad_hi', 'rad_lo'), ('longitudinal', 'long_hi', 'long_lo')):
-        out[name] = calculate_radlong_peaks(np.asarray(analysis[hi])[:nframes], np.asarray(analysis[lo])[:nframes],
-                                            frame_times, sys_frames, dia_frames, nframes, 'angle', pk.smooth_fraction,
-                                            pk.pad_len, pk.peak_thres, pk.min_dist, pk.pick_peak_by_subset)
+        out[name] = stage(lambda hi=hi, lo=lo: calculate_radlong_peaks(
+            np.asarray(analysis[hi])[:nframes], np.asarray(analysis[lo])[:nframes], frame_times, sys_frames, dia_frames,
+            nframes, 'angle', pk.smooth_fraction, pk.pad_len, pk.peak_thres, pk.min_dist, pk.pick_peak_by_subset))
     return out
 
 
 def indices_of(result: Dict[str, object]) -> Dict[str, object]:
     """Only the integer outcome of clip_waveform_indices (what the north star wants bit-exact)."""
-    pick = lambda d: {k: [int(i) for i in d[k]] for k in ('sys_i', 'e_i', 'l_i', 'a_i')}
+    def pick(d):
+        if 'raises' in d:
+            return dict(d)
+        return {k: [int(i) for i in d[k]] for k in ('sys_i', 'e_i', 'l_i', 'a_i')}
     return {'sys_frames': result['sys_frames'], 'dia_frames': result['dia_frames'],
             'single': pick(result['single']), 'radial': pick(result['radial']), 'longitudinal': pick(result['longitudinal'])}

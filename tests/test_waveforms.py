@@ -132,3 +132,22 @@ def test_clip_waveform_indices_runs_on_analysis_dict():
     assert set(out) == {'sys_frames', 'dia_frames', 'single', 'radial', 'longitudinal'}
     assert all(isinstance(i, int) for i in out['radial']['e_i'])
     assert out['sys_frames'] and out['dia_frames']
+
+
+def test_whole_chain_on_oracle_flow_equals_harness(oracle):
+    """a 64-frame synthetic clip solved by the CPU oracle, stored as fp16: the product's waveform pipeline fed with
+    the harness' waveforms gives the harness' indices (reference defaults everywhere) -- and the chain does not
+    degenerate on the synthetic clip (there ARE systole runs and peaks to compare)"""
+    from tee_optical_flow_b200.synth import make_clip, make_masks
+    n, h, w = 64, 120, 160
+    fr = make_clip(seed=0, n_frames=n, H=h, W=w, peak_disp=3.0, period=32.0)
+    masks = make_masks(0, n, h, w)
+    om = oracle.OracleDualTVL1(err_mode=0)
+    flows = [om.calc(fr[i], fr[i + 1]) for i in range(n - 1)]
+    flows.append(flows[-1])
+    f16 = (np.stack(flows) * np.float32(2.0)).astype(np.float16)
+    want = R.clip_indices(f16, masks["rv"], masks["av"], n - 2)
+    got = Wv.indices_of(Wv.clip_waveform_indices(want["waveforms"], n - 2, frame_rate=40.0))
+    for k in ("sys_frames", "dia_frames", "single", "radial", "longitudinal"):
+        assert got[k] == want[k], k
+    assert len(want["sys_frames"]) >= 1 and len(want["radial"]["e_i"]) >= 1
