@@ -1,6 +1,6 @@
 """OpticalFlowDataset mirror: the consumer-side contract of the producer's output
 (optical_flow/optical_flow_dataset.py:29-229), built from the in-memory HDF5 layout that
-``flow.process_frames`` returns (or from an HDF5 file when h5py is installed).
+``flow.process_frames`` returns, or from an HDF5 file through the package's own reader (hdf5.py).
 
 Same attribute names and semantics as the reference: ``vel_array`` = flow.astype(float32) (:57), ``nframes`` =
 attrs['nframes'] - 2 (:58), ``accel_array`` = np.gradient(vel, 1/frame_rate, axis=0) (:100), ``pwr_array`` = vel *
@@ -33,16 +33,18 @@ class OpticalFlowDataset:
                           {k: np.asarray(res[k]) for k in attrs['labels']})
 
     def _from_hdf5(self, path: str):
+        """the reference's constructor (optical_flow_dataset.py:45-111) on an HDF5 file, through the package's own
+        reader (hdf5.py) -- h5py is not needed"""
         import os
-        try:
-            import h5py
-        except ImportError as e:  # pragma: no cover
-            raise ImportError("h5py is required to open an HDF5 file; pass the dict from process_frames instead") from e
-        with h5py.File(path, 'r') as f:
-            attrs = dict(f['flow'].attrs)
-            self.filename = os.path.basename(path)[:-4]
-            masks = {k: f[k][()] for k in attrs['labels']}
-            self._init_common(f['flow'][()], f['echo'][()], attrs, masks)
+        from .hdf5 import read_hdf5
+        data, all_attrs = read_hdf5(path)
+        attrs = all_attrs['flow']
+        self.filename = os.path.basename(path)[:-4]
+        masks = {str(k): data[str(k)] for k in attrs['labels']}
+        self._init_common(data['flow'], data['echo'], attrs, masks)
+        if 'RWaveTime' in data:
+            self.RTimePresent = True
+            self.RWaveTimes = data['RWaveTime']
 
     def _init_common(self, flow, echo, attrs, masks):
         self.echo_array = echo
@@ -53,8 +55,9 @@ class OpticalFlowDataset:
         self.waveforms_present = bool(attrs['waveforms_present'])
         self.units_converted_flag = bool(attrs['units_converted'])
         if self.units_converted_flag:
-            self.frame_rate = attrs['frame_rate']
-            self.pixel_spacing = attrs['pixel_spacing']
+            # numpy scalars, as h5py hands attributes back: np.gradient's spacing type decides its working precision
+            self.frame_rate = np.asarray(attrs['frame_rate'])[()]
+            self.pixel_spacing = np.asarray(attrs['pixel_spacing'])[()]
             self.ID = attrs['ID']
         else:
             self.frame_rate = 1

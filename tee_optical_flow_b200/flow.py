@@ -166,21 +166,18 @@ def process_frames(frames: np.ndarray, mask_dict: Optional[Dict[str, np.ndarray]
 
 
 def save_hdf5(save_path: str, result: Dict[str, Any]) -> None:
-    """Writes process_frames' dict with the reference's dataset names, dtypes and gzip-9 (:399-472)."""
-    try:
-        import h5py
-    except ImportError as e:  # pragma: no cover
-        raise OpticalFlowCalculationError("h5py is not installed: the HDF5 container cannot be written here; "
-                                          "use the dict returned by process_frames") from e
+    """Writes process_frames' dict as the reference's container (:399-472): datasets 'echo', 'flow', one per saved mask
+    label (+ 'RWaveTime' when present), chunked + gzip-9, the attributes on 'flow'.  Uses the package's own HDF5 writer
+    (hdf5.py): h5py / libhdf5 are not needed."""
+    from .hdf5 import write_hdf5
     if os.path.exists(save_path):
         os.remove(save_path)
-    with h5py.File(save_path, 'w') as f:
-        f.create_dataset('echo', data=result['echo'], compression='gzip', compression_opts=9)
-        d = f.create_dataset('flow', data=result['flow'], compression='gzip', compression_opts=9)
-        for k in result['attrs']['labels']:
-            f.create_dataset(k, data=result[k], compression='gzip', compression_opts=9)
-        for k, v in result['attrs'].items():
-            d.attrs[k] = v if v is not None else np.nan
+    data = {'echo': result['echo'], 'flow': result['flow']}
+    for k in result['attrs']['labels']:
+        data[k] = np.asarray(result[k])
+    if 'RWaveTime' in result:
+        data['RWaveTime'] = np.asarray(result['RWaveTime'], dtype=np.float64)
+    write_hdf5(save_path, data, {'flow': dict(result['attrs'])})
 
 
 def extract_dicom_metadata(ds: Any, verbose: bool = False) -> Dict[str, Any]:
