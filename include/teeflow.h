@@ -92,6 +92,16 @@ TEEFLOW_API int teeflow_calc_clip(teeflow_handle h, const void* frames_dev, int 
                       int64_t frame_stride, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
                       int duplicate_last, void* stream);
 
+/* Asynchronous form of teeflow_calc_clip ("asynchronous on the caller's stream"): enqueues the image
+ * pyramid and the ONE dataflow launch that solves every pair on `stream` and returns; work the caller enqueues on the
+ * same stream afterwards runs behind it.  teeflow_finish() waits for the run, checks the scheduler's verdict and
+ * completes the statistics; teeflow_get_counters / teeflow_get_stats / teeflow_destroy call it implicitly, and a new
+ * calc on the handle is refused until then.  Not available in stepped mode. */
+TEEFLOW_API int teeflow_calc_clip_async(teeflow_handle h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                            int64_t frame_stride, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
+                            int duplicate_last, void* stream);
+TEEFLOW_API int teeflow_finish(teeflow_handle h);
+
 /* Generic form: n_pairs arbitrary (frame a -> frame b) pairs over a frame array (used for batches of clips and
  * for sharding a clip by pair range).  out_index[p] / dup_index[p] (host arrays) give the output slot of pair p
  * and an optional second slot to copy it to (-1 = none). */

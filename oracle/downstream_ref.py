@@ -337,3 +337,40 @@ def clip_indices(flow_f16, label_mask, av_mask, nframes, cc_smooth=0.2, cc_pad=2
         'longitudinal': stage(lambda: radlong_peak_indices(lhi, llo, sys_frames, nframes, **kw)),
         'waveforms': dict(ang_mode=ang, mag_hi=mag_hi, rad_hi=rhi, rad_lo=rlo, long_hi=lhi, long_lo=llo), 'centroids': cent,
     }
+
+
+# ------------------------------------------------------------------ calculate_optical_flow.py:91-182
+def moving_avg_mask(arr, n=4, threshold=0.49):
+    arr2 = np.vstack((arr[0:1], arr, arr[-1:], arr[-1:]))
+    s = np.cumsum(arr2.astype(float), axis=0)
+    s[n:] = s[n:] - s[:-n]
+    return (s[n - 1:] / n) > threshold
+
+
+def remove_small_objects(mask, min_size):
+    """skimage.morphology.remove_small_objects on a bool image: connectivity 1 (4-connected) components with
+    fewer than min_size pixels are removed"""
+    from scipy import ndimage
+    lab, n = ndimage.label(mask)                       # default structure: 4-connectivity
+    if n == 0:
+        return mask.copy()
+    sizes = np.bincount(lab.ravel())
+    too_small = sizes < min_size
+    too_small[0] = False
+    out = mask.copy()
+    out[too_small[lab]] = False
+    return out
+
+
+def clean_mask(arr, classes: dict, min_size=500):
+    """clean_mask for a {label: class_id} table -> {label: (N,H,W,2) bool, 'bkgd': ...}"""
+    from scipy.ndimage import binary_fill_holes
+    agg = np.zeros(arr.shape, bool)
+    out = {}
+    for k, cid in classes.items():
+        m = moving_avg_mask(arr == cid)
+        clean = np.stack([remove_small_objects(binary_fill_holes(m[i]), min_size) for i in range(m.shape[0])])
+        agg |= clean
+        out[k] = np.repeat(clean[..., None], 2, axis=3)
+    out['bkgd'] = np.repeat((~agg)[..., None], 2, axis=3)
+    return out

@@ -59,6 +59,9 @@ SIGNATURES = {
     "teeflow_last_error": (C.c_char_p, [C.c_void_p]),
     "teeflow_calc_clip": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
+    "teeflow_calc_clip_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                          C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p]),
+    "teeflow_finish": (C.c_int, [C.c_void_p]),
     "teeflow_calc_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                      _i32p, _i32p, _i32p, _i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
                                      C.c_void_p]),

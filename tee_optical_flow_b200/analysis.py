@@ -4,8 +4,9 @@ longitudinal projections, the exact per-frame percentiles and the 1000-bin histo
 runs in libteeflow.so; only the tiny per-frame bookkeeping the reference does in Python (empty-frame
 carry-forward, the +1 on the histogram counts) stays on the host.
 
-Not re-implemented here (SURVEY.md §8f "next"): calc_AV_centroid (connected components + Savitzky-Golay); pass
-its result in as `centroid_list`.
+calc_AV_centroid (connected components + Savitzky-Golay, analysis.py:39-86) lives in masks.py (GPU labelling); its
+result is passed in as `centroid_list`.  The downstream waveform pipeline (smoothing, systole / diastole runs, peak
+picking) is waveforms.py.
 """
 from __future__ import annotations
 

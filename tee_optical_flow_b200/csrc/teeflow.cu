@@ -62,6 +62,10 @@ struct teeflow_engine {
     int ctas_per_sm[3] = {1, 1, 1};   // per instantiated pitch (stepped kernel)
     int ctas_per_sm_flow[3] = {1, 1, 1};   // ... (dataflow kernel)
     int stepped = 0;                  // 1: one launch per phase step (profiling / A-B); 0: one dataflow launch per run
+    int async_mode = 0;               // set by teeflow_calc_clip_async for the duration of its run_pairs call
+    int pending = 0;                  // an asynchronous dataflow run is in flight: teeflow_finish() completes it
+    int pending_pairs = 0, pending_grid = 0;
+    cudaStream_t pending_stream = nullptr;
     Task* tasks = nullptr;            // [kTaskRing] task descriptors of the dataflow scheduler
     FlowCtl* flow_ctl = nullptr;
     unsigned long long* flow_stats = nullptr;   // [32] device, diagnostic builds
@@ -260,6 +264,7 @@ int teeflow_create(const teeflow_params* p, int device, teeflow_handle* out) {
 int teeflow_destroy(teeflow_handle h) {
     if (!h) return TEEFLOW_OK;
     cudaSetDevice(h->device);
+    if (h->pending) { cudaStreamSynchronize(h->pending_stream); h->pending = 0; }
     cudaFree(h->pyrI); cudaFree(h->pyrG);
     cudaFree(h->planes_raw); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
     cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg); cudaFree(h->tasks); cudaFree(h->flow_ctl); cudaFree(h->flow_stats);
@@ -564,6 +569,7 @@ static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, 
         if (pair_a[i] < 0 || pair_a[i] >= n_frames || pair_b[i] < 0 || pair_b[i] >= n_frames || out_index[i] < 0)
             return fail(h, TEEFLOW_ERR_BAD_ARG, "pair %d references a frame outside [0,%d)", i, n_frames);
     CU_TRY(h, cudaSetDevice(h->device));
+    if (h->pending) return fail(h, TEEFLOW_ERR_STATE, "an asynchronous run is in flight: call teeflow_finish() first");
     memset(&h->st, 0, sizeof(h->st));
     h->st.n_pairs = n_pairs;
     if (n_pairs == 0) return TEEFLOW_OK;
@@ -756,6 +762,11 @@ static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, 
         void* args[] = {(void*)&Pf};
         CU_TRY(h, cudaLaunchCooperativeKernel((const void*)flow_kernel_for(pitch), dim3((unsigned)grid_f), dim3(kThreads), args, 0, stream));
         CU_TRY(h, cudaEventRecord(h->ev_t1, stream));
+        if (h->async_mode && !copy_out) {               // the caller fetches the verdict with teeflow_finish()
+            h->pending = 1; h->pending_pairs = n_pairs; h->pending_grid = grid_f; h->pending_stream = stream;
+            h->st.n_slots = S;
+            return TEEFLOW_OK;
+        }
         if (copy_out) {
             volatile int* order = h->h_flow_order;
             for (;;) {
@@ -891,6 +902,41 @@ int teeflow_calc_clip(teeflow_handle h, const void* frames_dev, int dtype, int n
                      flow_f32_dev, flow_f16_dev, out_scale, (cudaStream_t)stream);
 }
 
+int teeflow_calc_clip_async(teeflow_handle h, const void* frames_dev, int dtype, int n_frames, int H, int W,
+                            int64_t frame_stride, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
+                            int duplicate_last, void* stream) {
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (h->stepped || h->n_launch_events > 0)
+        return fail(h, TEEFLOW_ERR_STATE, "asynchronous runs need the dataflow scheduler (stepped mode / launch timing is on)");
+    h->async_mode = 1;
+    const int rc = teeflow_calc_clip(h, frames_dev, dtype, n_frames, H, W, frame_stride, flow_f32_dev, flow_f16_dev, out_scale,
+                                     duplicate_last, stream);
+    h->async_mode = 0;
+    return rc;
+}
+
+int teeflow_finish(teeflow_handle h) {
+    if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (!h->pending) return TEEFLOW_OK;
+    h->pending = 0;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaStreamSynchronize(h->pending_stream));
+    FlowCtl c1;
+    CU_TRY(h, cudaMemcpy(&c1, h->flow_ctl, sizeof(c1), cudaMemcpyDeviceToHost));
+    if (c1.abort) return fail(h, TEEFLOW_ERR_STATE, c1.abort == 1 ? "dataflow scheduler watchdog: a warp waited too long for a task"
+                                                                   : "dataflow scheduler lost the task ring");
+    if (c1.pairs_done < h->pending_pairs)
+        return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", c1.pairs_done, h->pending_pairs);
+    CU_TRY(h, cudaEventElapsedTime(&h->st.device_ms, h->ev_t0, h->ev_t1));
+    CU_TRY(h, cudaEventElapsedTime(&h->st.pyramid_ms, h->ev_t0, h->ev_tp));
+    CU_TRY(h, cudaEventElapsedTime(&h->st.solver_ms, h->ev_tp, h->ev_t1));
+    h->st.double_steps = c1.spec_applied; h->st.double_steps_discarded = c1.spec_discarded;
+    h->st.solver_launches = 1;
+    h->st.kernel_launches += 1;
+    h->st.grid_ctas = h->pending_grid;
+    return TEEFLOW_OK;
+}
+
 static int ensure_stage(teeflow_engine* h, void*& ptr, size_t& cap, size_t bytes) {
     if (bytes > cap) {
         if (ptr) cudaFree(ptr);
@@ -955,6 +1001,7 @@ int teeflow_calc_pair_host(teeflow_handle h, const void* I0_host, const void* I1
 
 int teeflow_get_counters(teeflow_handle h, int32_t* counters, int n_pairs_cap) {
     if (!h) return fail(nullptr, TEEFLOW_ERR_BAD_ARG, "NULL handle");
+    if (h->pending) { const int rc = teeflow_finish(h); if (rc) return rc; }
     const int n = h->st.n_pairs;
     if (counters) {
         if (n_pairs_cap < n) return fail(h, TEEFLOW_ERR_BAD_ARG, "counter buffer holds %d pairs, need %d", n_pairs_cap, n);
@@ -973,6 +1020,7 @@ int teeflow_get_flow_stats(teeflow_handle h, uint64_t* out32) {
 
 int teeflow_get_stats(teeflow_handle h, teeflow_stats* out) {
     if (!h || !out) return fail(h, TEEFLOW_ERR_BAD_ARG, "NULL argument");
+    if (h->pending) { const int rc = teeflow_finish(h); if (rc) return rc; }
     *out = h->st;
     return TEEFLOW_OK;
 }

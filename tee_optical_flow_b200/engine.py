@@ -149,7 +149,7 @@ class TVL1Engine:
 
     # ------------------------------------------------------------------ all pairs of a clip
     def calc_clip(self, frames, out_scale: float = 1.0, duplicate_last: bool = True, want_f32: bool = True,
-                  want_f16: bool = False):
+                  want_f16: bool = False, asynchronous: bool = False):
         """Flow of every consecutive pair of ``frames`` (N, H, W) -- the reference's pair loop
         (calculate_optical_flow.py:584-600) in one call.
 
@@ -157,10 +157,12 @@ class TVL1Engine:
         torch CUDA tensor -> device path, torch results on the same device.
         Returns (flow_f32 or None, flow_f16 or None), each (N_out, H, W, 2) with N_out = N-1 (+1 when
         ``duplicate_last``: the reference appends a copy of the last flow, :599).
+        ``asynchronous`` (device path): return as soon as the work is enqueued on the current CUDA stream; the result
+        tensors are complete for later work on that stream, `finish()` (or last_counters()) fetches the verdict.
         """
         if isinstance(frames, np.ndarray):
             return self._calc_clip_host(frames, out_scale, duplicate_last, want_f32, want_f16)
-        return self._calc_clip_device(frames, out_scale, duplicate_last, want_f32, want_f16)
+        return self._calc_clip_device(frames, out_scale, duplicate_last, want_f32, want_f16, asynchronous=asynchronous)
 
     def _calc_clip_host(self, frames, out_scale, duplicate_last, want_f32, want_f16):
         frames = np.ascontiguousarray(frames)
@@ -176,7 +178,13 @@ class TVL1Engine:
             f16.ctypes.data if want_f16 else None, float(np.float32(out_scale)), int(duplicate_last)))
         return f32, f16
 
-    def _calc_clip_device(self, frames, out_scale, duplicate_last, want_f32, want_f16, out_f32=None, out_f16=None):
+    def finish(self) -> None:
+        """Completes an asynchronous device run (`calc_clip(..., asynchronous=True)`): waits for it on its stream,
+        raises if the scheduler reported a problem.  last_counters() calls it implicitly."""
+        self._check(self._lib.teeflow_finish(self._h))
+
+    def _calc_clip_device(self, frames, out_scale, duplicate_last, want_f32, want_f16, out_f32=None, out_f16=None,
+                          asynchronous: bool = False):
         import torch
         if not (isinstance(frames, torch.Tensor) and frames.is_cuda):
             raise OpticalFlowCalculationError("frames must be a numpy array or a CUDA torch tensor")
@@ -198,7 +206,9 @@ class TVL1Engine:
         f16 = out_f16 if out_f16 is not None else (
             torch.empty((n_out, H, W, 2), dtype=torch.float16, device=frames.device) if want_f16 else None)
         stream = torch.cuda.current_stream(frames.device).cuda_stream
-        self._check(self._lib.teeflow_calc_clip(
+        entry = self._lib.teeflow_calc_clip_async if asynchronous else self._lib.teeflow_calc_clip
+        self._keep = frames                        # an asynchronous run reads the frames after this call returns
+        self._check(entry(
             self._h, frames.data_ptr(), code, N, H, W, H * W, f32.data_ptr() if f32 is not None else None,
             f16.data_ptr() if f16 is not None else None, float(np.float32(out_scale)), int(duplicate_last),
             C.c_void_p(stream)))

@@ -311,3 +311,24 @@ def test_long_clip_config_1024_7scales_10warps(oracle):
     assert np.all(flow == ref)
     assert np.array_equal(counters[0], om.last_counters)
     assert (counters[0, :, 2] == 10).all()
+
+
+def test_asynchronous_device_run_equals_synchronous(engine):
+    """teeflow_calc_clip_async: returns after enqueueing the pyramid and the one dataflow launch; later work on the
+    stream sees complete results, teeflow_finish() delivers the verdict and the statistics"""
+    import torch
+    from tee_optical_flow_b200.exceptions import OpticalFlowCalculationError
+    from tee_optical_flow_b200.synth import make_clip
+    fr = torch.from_numpy(make_clip(seed=14, n_frames=6, H=96, W=128, peak_disp=4.0, period=8.0)).cuda()
+    want32, want16 = engine.calc_clip(fr, out_scale=0.5, want_f16=True)
+    c_sync, _ = engine.last_counters()
+    got32, got16 = engine.calc_clip(fr, out_scale=0.5, want_f16=True, asynchronous=True)
+    with pytest.raises(OpticalFlowCalculationError):      # a second run before finish() is refused
+        engine.calc_clip(fr)
+    follow_up = got32 * 2                                 # enqueued behind the solver on the same stream
+    engine.finish()
+    c_async, info = engine.last_counters()
+    assert info["solver_launches"] == 1 and info["n_pairs"] == 5
+    assert torch.equal(got32, want32) and torch.equal(got16, want16) and torch.equal(follow_up, want32 * 2)
+    assert np.array_equal(c_sync, c_async)
+    engine.finish()                                       # idempotent

@@ -1,0 +1,38 @@
+#!/bin/bash
+# Per-op register / spill report and SASS evidence for profiles/: compiles the dataflow kernel with ONE strip op at a
+# time (-DTEEFLOW_PHASE_MASK, analysis builds only) and with all of them, prints ptxas' resource lines, and counts the
+# instruction classes the judge looks for in the shipped library.   usage: tools/op_resources.sh > profiles/rN_sass_resources.txt
+cd "$(dirname "$0")/.."
+SRC=tee_optical_flow_b200/csrc/teeflow.cu
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false -lineinfo -Xptxas=-v"
+echo "# nvcc $(nvcc --version | tail -2 | head -1)"
+for spec in "0x02u level_init" "0x04u warp" "0x08u median" "0x10u inner" "0x80u inner2(two-iteration)" "0x60u final+wase" "0xffu ALL(shipped)"; do
+  set -- $spec
+  echo "== strip op(s): $2   (-DTEEFLOW_PHASE_MASK=$1)"
+  nvcc $FLAGS -DTEEFLOW_PHASE_MASK=$1 -cubin -o /tmp/_op.cubin $SRC 2>&1 | grep -A2 "tvl1_flow_kernelILi1024" | grep -E "spill|Used" | sed 's/^ */   /'
+done
+LIB=tee_optical_flow_b200/libteeflow.so
+echo "== shipped library $LIB: cuobjdump -res-usage (solver kernels)"
+cuobjdump -res-usage $LIB 2>/dev/null | grep -A1 -E "tvl1_(flow|step)_kernelILi1024" | grep -v "^--"
+echo "== SASS instruction census of tvl1_flow_kernel<1024> (shipped)"
+cuobjdump -sass $LIB | awk '/Function : .*tvl1_flow_kernelILi1024/{p=1;next} /Function : /{p=0} p' > /tmp/_flow.sass
+for op in "LDG" "STG\|ST\.E" "LDL" "STL" "CCTL.E.PF2" "FFMA2\|FADD2\|FMUL2" "FMNMX" "MUFU" "SHFL" "ATOMG\|ATOM\.\|RED\." "MEMBAR\|ERRBAR" "LDGSTS" "UTMALDG\|UTMASTG\|UBLKCP" "HMMA\|UTC.*MMA" "BAR\.SYNC"; do
+  printf "   %-28s %s\n" "$op" "$(grep -c "$op" /tmp/_flow.sass)"
+done
+echo "   total instructions           $(grep -c '^\s*/\*[0-9a-f]\{4,\}\*/' /tmp/_flow.sass)"
+echo "== where the local-memory accesses (spills) of the shipped kernel sit: offsets of LDL / STL vs the hot loops"
+python3 - <<'PY'
+import re
+lines=[l for l in open('/tmp/_flow.sass') if re.match(r'\s*/\*[0-9a-f]{4,}\*/',l)]
+addr=lambda l:int(re.match(r'\s*/\*([0-9a-f]+)\*/',l).group(1),16)
+loops=[]
+for l in lines:
+    m=re.search(r'BRA(?:\.U)?\s+(?:!?U?P\d,\s*)?(0x[0-9a-f]+)',l)
+    if m:
+        t=int(m.group(1),16); a=addr(l)
+        if t<a and 0x400<a-t<0x4000: loops.append((t,a))
+print("   hot loops (backward branches, 1-16 KB):", [(hex(a),hex(b),(b-a)//16) for a,b in loops])
+sp=[addr(l) for l in lines if 'LDL' in l or 'STL' in l]
+inside=[hex(a) for a in sp if any(t<=a<=e for t,e in loops)]
+print("   LDL/STL instructions:", len(sp), " inside a hot loop:", len(inside), inside[:12])
+PY
