@@ -55,6 +55,15 @@ constexpr int kPF = TEEFLOW_PF_ROWS;   // inner iteration: rows ahead of the cur
 #ifndef TEEFLOW_DYNAMIC_ITEMS
 #define TEEFLOW_DYNAMIC_ITEMS 1
 #endif
+// 1: the CB plane holds only rho_c, two image rows per float2 -- element x of the CB row of an EVEN image row y is
+// (rho_c(x, y), rho_c(x, y + 1)) -- and the inner iteration recomputes grad = I1wx^2 + I1wy^2 from the CA plane (the
+// same two products and one sum the warp op rounded): 60 instead of 64 bytes per pixel and iteration.
+// 0: CB = (grad, rho_c) per pixel.
+#ifndef TEEFLOW_RHO_PACK
+#define TEEFLOW_RHO_PACK 1
+#endif
+constexpr bool kRhoPack = TEEFLOW_RHO_PACK != 0;
+static_assert(!kRhoPack || (kIR % 2 == 0 && kIR2 % 2 == 0 && kPR % 2 == 0), "row-pair packing of rho_c needs even strip heights");
 
 // ------------------------------------------------------------------------------------------------ pyramid
 // level 0: convertTo(CV_32F, 1) for u8, x255 for f32 (tvl1flow.cpp: I0mult / I1mult)
@@ -247,6 +256,7 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
     // the flow / I0 of the next row are fetched while the current row's gather runs (one row ahead)
     float2 u_n = __ldcg(row + oU);
     float i0_n = __ldg(I0 + (unsigned)(y0 * g.W + x));
+    float rho_even = 0.f;                        // kRhoPack: rho_c of the even row above
     for (int y = y0; y < y1; ++y) {
         const unsigned q = (unsigned)(y * g.W + x);
         const float2 u = u_n;
@@ -262,7 +272,14 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
         const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic, P.negzero);
         const float Ix2 = w.y * w.y, Iy2 = w.z * w.z;
         row[PL_CA * PITCH] = make_float2(w.y, w.z);
-        row[PL_CB * PITCH] = make_float2(Ix2 + Iy2, (w.x - w.y * u.x - w.z * u.y - i0));
+        const float rho_c = w.x - w.y * u.x - w.z * u.y - i0;
+        if (kRhoPack) {                          // strips start on even rows: the pair (y - 1, y) is written from row y
+            if (y & 1) row[(int)(PL_CB * PITCH) - (int)L::ROW] = make_float2(rho_even, rho_c);
+            else if (y + 1 == g.H) row[PL_CB * PITCH] = make_float2(rho_c, 0.f);
+            rho_even = rho_c;
+        } else {
+            row[PL_CB * PITCH] = make_float2(Ix2 + Iy2, rho_c);
+        }
         row += L::ROW;
     }
 }
@@ -352,16 +369,22 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
 // the scalar operation of the C++ source.  Each piece has a branch-free FAST form that also reports whether its
 // result can be trusted (operands inside the domain on which the fast sequence is proven exact) and an EXACT form
 // (IEEE division, double-precision hypot); a row takes one merged branch to the exact forms when any lane needs it.
-struct InnerRow { float2 u, ca, cb, px, py, pxl; };   // ca = (I1wx, I1wy), cb = (grad, rho_c)
+// ca = (I1wx, I1wy), cb = (grad, rho_c); kRhoPack: cb = (rho_c of the even row of the pair, rho_c of the odd row)
+struct InnerRow { float2 u, ca, cb, px, py, pxl; };
 struct InnerConst { float l_t, theta, taut, negzero; };
 
 // estimateV: d = v - u.  c3_bad: the thresholding division ran outside the fast path's domain (needs_exact).
 struct VStep { float2 d; float nrho, grad; bool bad; };
-__device__ __forceinline__ VStep estimate_v_fast(const InnerRow& r, const InnerConst& K) {
+__device__ __forceinline__ VStep estimate_v_fast(const InnerRow& r, const InnerConst& K, bool odd_row) {
     VStep o;
     const float2 cu = mul2(r.ca, r.u);
-    const float rho = r.cb.y + (cu.x + cu.y);
-    const float grad = r.cb.x;
+    float rho_c = r.cb.y, grad = r.cb.x;
+    if (kRhoPack) {                              // I1wx^2 + I1wy^2, rounded like the warp op's Ix2 + Iy2
+        rho_c = odd_row ? r.cb.y : r.cb.x;
+        const float2 sq = mul2_nofuse(r.ca, r.ca, K.negzero);
+        grad = sq.x + sq.y;
+    }
+    const float rho = rho_c + (cu.x + cu.y);
     const float lg = K.l_t * grad;
     const bool c1 = rho < -lg;
     const bool c2 = !c1 && rho > lg;
@@ -393,8 +416,8 @@ __device__ __forceinline__ float2 theta_div_px(const InnerRow& r, float2 pxl, fl
 
 // estimateV + divergence + estimateU for one pixel (tvl1flow.cpp order of operations), self-contained form
 __device__ __forceinline__ float2 estimate_u_px(const InnerRow& r, float2 pxl, float2 pyu, bool strip_at_x0,
-                                                bool first_col_not_first_row, const InnerConst& K) {
-    VStep v = estimate_v_fast(r, K);
+                                                bool first_col_not_first_row, const InnerConst& K, bool odd_row) {
+    VStep v = estimate_v_fast(r, K, odd_row);
     if (v.bad) v.d = estimate_v_exact(r, v);
     return add2(add2(r.u, v.d), theta_div_px(r, pxl, pyu, strip_at_x0, first_col_not_first_row, K));
 }
@@ -521,12 +544,14 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         else return const_cast<char*>(p) + dp;
     };
     auto st = [](char* p, int off, float2 v) { *reinterpret_cast<float2*>(p + off) = v; };
-    auto load_row = [&](int rows_ahead) {
+    // kRhoPack: an odd image row shares the CB element of the even row above it (`above`): no load
+    auto load_row = [&](int rows_ahead, bool odd, float2 above) {   // odd: parity of the loaded image row (warp-uniform)
         const int d = rows_ahead * ROWB;
         InnerRow r;
         r.u = ld(pu, d);
         r.ca = ld(pc, d);
-        r.cb = ld(pc, d + PB);
+        r.cb = above;
+        if (!kRhoPack || !odd) r.cb = ld(pc, d + PB);
         r.px = ld(pp, d);
         r.py = ld(pp, d + 2 * PB);
         r.pxl = make_float2(0.f, 0.f);
@@ -536,9 +561,10 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     // The register look-ahead is one row (~1.5 us of work per warp); under load a DRAM access takes about as long, and
     // with the other phases' warps on the SM too few bytes are in flight (the first use of the next row's loads was
     // the kernel's top stall).  Rows further ahead are therefore pulled into L2 -- no registers, five instructions.
-    auto prefetch_row = [&](int rows_ahead) {
+    auto prefetch_row = [&](int rows_ahead, bool odd) {
         const int d = rows_ahead * ROWB;
-        prefetch_l2(pu + d); prefetch_l2(pc + d); prefetch_l2(pc + d + PB); prefetch_l2(pp + d); prefetch_l2(pp + d + 2 * PB);
+        prefetch_l2(pu + d); prefetch_l2(pc + d); prefetch_l2(pp + d); prefetch_l2(pp + d + 2 * PB);
+        if (!kRhoPack || !odd) prefetch_l2(pc + d + PB);
     };
     // left neighbour's px: by shuffle, lane 0 takes the value it loaded itself (zero at the image border)
     auto left_px = [&](const InnerRow& r) {
@@ -554,14 +580,14 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     double err = 0.0;
     float2 pyu = make_float2(0.f, 0.f);
     if (y0 > 0) pyu = ld(pp, 2 * PB - ROWB);
-    const InnerRow cur = load_row(0);
-    InnerRow row = load_row(1);                  // row y0 + 1 <= H: inside the image or the first pad row
+    const InnerRow cur = load_row(0, false, make_float2(0.f, 0.f));     // y0 is even (kIR is)
+    InnerRow row = load_row(1, true, cur.cb);    // row y0 + 1 <= H: inside the image or the first pad row
     if (kPF > 0) {
 #pragma unroll
-        for (int k = 2; k < kPF; ++k) if (y0 + k < y1) prefetch_row(k);
+        for (int k = 2; k < kPF; ++k) if (y0 + k < y1) prefetch_row(k, (k & 1) != 0);
     }
 
-    float2 un = estimate_u_px(cur, left_px(cur), pyu, strip_at_x0, first_col && y0 > 0, K);
+    float2 un = estimate_u_px(cur, left_px(cur), pyu, strip_at_x0, first_col && y0 > 0, K, false);
     if (owner) {
         st(partner_u(pu), 0, un);
         const float2 du = sub2(un, cur.u);
@@ -577,10 +603,11 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     // waited for the very load it was meant to hide -- 22 % of all stall samples of the run on one MOV.)
 #pragma unroll kInnerUnroll
     for (int y = y0; y < y1 - 1; ++y) {
-        const InnerRow nxt = load_row(2);
-        if (kPF > 0 && y + kPF < y1) prefetch_row(kPF);
+        const bool y_odd = (y & 1) != 0;         // row y + 2 has the parity of y, row y + 1 the other one
+        const InnerRow nxt = load_row(2, y_odd, row.cb);
+        if (kPF > 0 && y + kPF < y1) prefetch_row(kPF, ((y + kPF) & 1) != 0);
         // u_new of row y+1, then forwardGradient(u_new) + estimateDualVariables of row y -- fast forms
-        VStep v = estimate_v_fast(row, K);
+        VStep v = estimate_v_fast(row, K, !y_odd);
         const float2 tdv = theta_div_px(row, left_px(row), py_c, strip_at_x0, first_col, K);
         float2 un_n = add2(add2(row.u, v.d), tdv);
         const float2 ux = diff_x(un);
@@ -618,7 +645,7 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     {
         float2 uy = make_float2(0.f, 0.f);
         if (y1 < H) {                            // warp-uniform
-            const float2 un_n = estimate_u_px(row, left_px(row), py_c, strip_at_x0, first_col, K);
+            const float2 un_n = estimate_u_px(row, left_px(row), py_c, strip_at_x0, first_col, K, (y1 & 1) != 0);
             uy = sub2(un_n, un);
         }
         const float2 ux = diff_x(un);
@@ -680,21 +707,23 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
 
     auto ld = [](const char* p, int off) { return __ldcg(reinterpret_cast<const float2*>(p + off)); };
     auto st = [](const char* p, int off, float2 v) { *reinterpret_cast<float2*>(const_cast<char*>(p) + off) = v; };
-    auto load_row = [&](int rows_ahead) {
+    auto load_row = [&](int rows_ahead, bool odd, float2 above) {   // see op_inner
         const int d = rows_ahead * ROWB;
         InnerRow r;
         r.u = ld(pu, d);
         r.ca = ld(pc, d);
-        r.cb = ld(pc, d + PB);
+        r.cb = above;
+        if (!kRhoPack || !odd) r.cb = ld(pc, d + PB);
         r.px = ld(pp, d);
         r.py = ld(pp, d + 2 * PB);
         r.pxl = make_float2(0.f, 0.f);
         if (lane0_left) r.pxl = ld(pp, d - 8);
         return r;
     };
-    auto prefetch_row = [&](int rows_ahead) {    // into L2, see op_inner
+    auto prefetch_row = [&](int rows_ahead, bool odd) {    // into L2, see op_inner
         const int d = rows_ahead * ROWB;
-        prefetch_l2(pu + d); prefetch_l2(pc + d); prefetch_l2(pc + d + PB); prefetch_l2(pp + d); prefetch_l2(pp + d + 2 * PB);
+        prefetch_l2(pu + d); prefetch_l2(pc + d); prefetch_l2(pp + d); prefetch_l2(pp + d + 2 * PB);
+        if (!kRhoPack || !odd) prefetch_l2(pc + d + PB);
     };
     auto diff_x = [&](float2 v) {                // forward x-difference (zero in the last image column)
         const float2 d = sub2(make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1)), v);
@@ -713,14 +742,16 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
     float2 u2p = zero2;                                       // u'' of row r-2 (when a step starts)
     float2 ca_p = zero2, cb_p = zero2, px_p = zero2;          // inputs of row r-1
     float2 py_p = ra >= 1 ? ld(pp, 2 * PB - ROWB) : zero2;
-    InnerRow row = load_row(0);                               // row ra
+    // row ra; kRhoPack: an odd first row takes the CB element of the (even) row above it
+    InnerRow row = load_row(0, (ra & 1) != 0, (kRhoPack && (ra & 1)) ? ld(pc, PB - ROWB) : zero2);
 
 #pragma unroll 1
     for (int r = ra; r <= y1 + 1; ++r) {
         const bool has_a = r <= re;                            // row r exists (warp-uniform)
         InnerRow nxt = row;
-        if (r < re) nxt = load_row(1);                         // row r + 1 is in flight while this step computes
-        if (kPF > 0 && r + kPF <= re) prefetch_row(kPF);
+        const bool r_odd = (r & 1) != 0;
+        if (r < re) nxt = load_row(1, !r_odd, row.cb);         // row r + 1 is in flight while this step computes
+        if (kPF > 0 && r + kPF <= re) prefetch_row(kPF, ((r + kPF) & 1) != 0);
         float2 u1 = zero2;
         if (has_a) {
             // A(r): estimateV + divergence(p) + estimateU, first iteration
@@ -728,7 +759,7 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
             in.pxl = make_float2(and_or(__shfl_up_sync(0xffffffffu, row.px.x, 1), shfl_left, row.pxl.x),
                                  and_or(__shfl_up_sync(0xffffffffu, row.px.y, 1), shfl_left, row.pxl.y));
             const float2 pyu = r >= 1 ? py_p : zero2;
-            VStep v = estimate_v_fast(in, K);
+            VStep v = estimate_v_fast(in, K, r_odd);
             if (v.bad) v.d = estimate_v_exact(in, v);
             u1 = add2(add2(in.u, v.d), theta_div_px(in, in.pxl, pyu, strip_at_x0, first_col && r > 0, K));
             if (owner && r >= y0 && r < y1) e1 += sq_norm(u1, in.u);
@@ -746,7 +777,7 @@ __device__ __forceinline__ void op_inner2(const EngineParams& P, int level, int 
                 in.u = u1p; in.ca = ca_p; in.cb = cb_p; in.px = n1x; in.py = n1y;
                 in.pxl = left_of(n1x);
                 const float2 pyu = q >= 1 ? p1y : zero2;
-                VStep v = estimate_v_fast(in, K);
+                VStep v = estimate_v_fast(in, K, !r_odd);     // row q = r - 1
                 if (v.bad) v.d = estimate_v_exact(in, v);
                 u2 = add2(add2(u1p, v.d), theta_div_px(in, in.pxl, pyu, strip_at_x0, first_col && q > 0, K));
                 if (owner && q < y1) { st(pu, du - ROWB, u2); e2 += sq_norm(u2, u1p); }
@@ -860,6 +891,12 @@ __device__ __forceinline__ bool needs_l1_acquire(int phase) { return phase == PH
 
 #ifndef TEEFLOW_FLOW_STATS
 #define TEEFLOW_FLOW_STATS 0
+#endif
+#ifndef TEEFLOW_EARLY_TICKET
+#define TEEFLOW_EARLY_TICKET 0   // dataflow scheduler: request the next strip ticket when a strip starts (not when it ends)
+#endif
+#ifndef TEEFLOW_EARLY_PROBE
+#define TEEFLOW_EARLY_PROBE 1    // dataflow scheduler: read the task descriptors at the cursor before the release fence
 #endif
 #ifndef TEEFLOW_PHASE_MASK
 #define TEEFLOW_PHASE_MASK 0xffu
@@ -1104,6 +1141,13 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
     if (lane == 0) t = atomicAdd(&F->ticket, 1u);
     unsigned pend_arrive = 0, pend_n = 0;              // pend_n == 0: nothing pending
     int pend_slot = 0, pend_phase = 0;
+#if TEEFLOW_EARLY_TICKET
+    unsigned t_next = 0;                               // lane 0: the ticket after t, requested when strip t starts
+#endif
+#if TEEFLOW_EARLY_PROBE
+    uint4 d_early = make_uint4(0u, 0u, 0u, 0u);        // descriptors at the cursor, read before the release fence
+    bool have_early = false;
+#endif
 
     for (;;) {
         t = __shfl_sync(0xffffffffu, t, 0);
@@ -1111,7 +1155,13 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
         uint4 desc = make_uint4(0u, 0u, 0u, 0u);
         for (bool first_probe = true;; first_probe = false) {
             const Task* q = P.tasks + ((kc + (unsigned)lane) & (kTaskRing - 1u));
-            const uint4 d = ld_volatile_v4(q);         // the whole descriptor: one 16-byte store of the publisher
+            // the whole descriptor: one 16-byte store of the publisher.  A published descriptor never changes, so the
+            // copy read before the previous strip's fence serves the first probe (kc has not moved since)
+#if TEEFLOW_EARLY_PROBE
+            const uint4 d = (first_probe && have_early) ? d_early : ld_volatile_v4(q);
+#else
+            const uint4 d = ld_volatile_v4(q);
+#endif
             const unsigned want = kc + (unsigned)lane + 1u;
             const bool pub = d.x == want;
             const bool mine = pub && (((d.z >> 20) & 0xfu) == (unsigned)PH_EXIT || (t - d.y) < (d.z & kTaskItemsMax));
@@ -1164,19 +1214,33 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
         const int strip = (int)(t - desc.y);
         if (needs_l1_acquire(phase)) __threadfence();  // plain (L1) plane reads ahead: drop the SM's stale lines
         const float bg = (phase == PH_FINAL && P.wase_w) ? __ldcg(P.bg_out + pair) : 0.f;
+#if TEEFLOW_EARLY_TICKET
+        // the next ticket travels while this strip runs.  (Still deadlock free: a warp that WAITS for a task holds no
+        // other ticket, and a ticket held in advance sits behind a strip that runs to its end without waiting.)
+        if (lane == 0) t_next = atomicAdd(&F->ticket, 1u);
+#endif
         TF_STAT(10)
 
         double err = 0.0, aux = 0.0;
         run_strip<PITCH>(P, phase, level, ucur, pcur, pair, bg, slot, strip, lane, s_cubic, err, aux);
         __syncwarp();
         TF_STAT(phase)
+#if TEEFLOW_EARLY_PROBE
+        // the probe of the next ticket's descriptor is in flight while lane 0's fence drains this strip's stores
+        d_early = ld_volatile_v4(P.tasks + ((kc + (unsigned)lane) & (kTaskRing - 1u)));
+        have_early = true;
+#endif
         if (lane == 0) {
             if (phase == PH_INNER) P.partial[(size_t)slot * P.max_tiles + strip] = err;
             if (phase == PH_WASE || phase == PH_INNER2) {
                 P.partial[(size_t)slot * P.max_tiles + 2 * strip] = err;
                 P.partial[(size_t)slot * P.max_tiles + 2 * strip + 1] = aux;
             }
+#if TEEFLOW_EARLY_TICKET
+            t = t_next;
+#else
             t = atomicAdd(&F->ticket, 1u);             // travels while the fence below drains this strip's stores
+#endif
             __threadfence();
             pend_arrive = atomicAdd(P.arrive + slot, 1u);
         }
