@@ -249,6 +249,11 @@ def phase_probe(frames_dev, device):
     return out
 
 
+def _make_clip_job(nf, seed):
+    from tee_optical_flow_b200.synth import make_clip
+    return make_clip(seed=seed, n_frames=nf, H=H, W=W)
+
+
 def strong_scaling(args, eng, dev, world, rank):
     """BASELINE config 4 in miniature: a FIXED batch of clips split over the ranks, every rank's share through one
     scheduler run (slots freed by one clip are refilled from the next), then the all-gather of the per-frame
@@ -263,14 +268,46 @@ def strong_scaling(args, eng, dev, world, rank):
         mine = list(range(lo, hi))
     else:
         mine = list(range(rank, B - B % world, world))
-    clips = np.stack([make_clip(seed=c, n_frames=nf, H=H, W=W) for c in mine])
-    d = torch.from_numpy(clips).to(dev)
+    # clip c of the batch is the synthetic clip of seed c % distinct (a 64-frame clip takes ~10 s of host time to
+    # synthesise, so a 256-clip batch reuses `distinct` seeds).  The node's ranks split the synthesis between them
+    # (rank r makes every world-th seed, in parallel processes) and exchange the clips through a cache directory.
+    import tempfile
+    distinct = min(args.distinct if args.distinct > 0 else B, B)
+    cache = Path(tempfile.gettempdir()) / "teeflow_bench_clips"
+    cache.mkdir(exist_ok=True)
+    path_of = lambda sd: cache / f"seed{sd}_{nf}x{H}x{W}.npy"
+    all_seeds = sorted({c % distinct for c in range(B - B % world)})
+    todo = [sd for sd in all_seeds[rank::world] if not path_of(sd).exists()]
+    t_gen = time.perf_counter()
+    if len(todo) > 1:
+        import multiprocessing as mp
+        from functools import partial
+        procs = max(1, min(len(todo), (os.cpu_count() or 8) // max(int(os.environ.get("LOCAL_WORLD_SIZE", world)), 1)))
+        with mp.get_context("spawn").Pool(procs) as pool:
+            made = pool.map(partial(_make_clip_job, nf), todo)
+    else:
+        made = [_make_clip_job(nf, sd) for sd in todo]
+    for sd, arr in zip(todo, made):
+        tmp = cache / f".tmp{rank}_{sd}.npy"
+        np.save(tmp, arr)
+        os.replace(tmp, path_of(sd))
+    del made
+    if world > 1:
+        dist.barrier()
+    t_gen = time.perf_counter() - t_gen
+    by_seed = {sd: np.load(path_of(sd)) for sd in sorted({c % distinct for c in mine})}
+    d = torch.empty((len(mine), nf, H, W), dtype=torch.uint8, device=dev)
+    for i, c in enumerate(mine):
+        d[i].copy_(torch.from_numpy(by_seed[c % distinct]))
+    del by_seed
     out16 = None
+    info_last = {}
 
     def step():
         nonlocal out16
         _, out16 = eng.calc_batch(d, want_f32=False, want_f16=True)
-        counters, _ = eng.last_counters()
+        nonlocal info_last
+        counters, info_last = eng.last_counters()
         rows = counters[:, :, 0].sum(axis=1, keepdims=True).astype(np.float64)       # inner iterations per pair
         if world > 1:                                                               # every rank: len(mine) * (nf-1) rows
             buf = torch.from_numpy(rows).to(dev)
@@ -302,10 +339,12 @@ def strong_scaling(args, eng, dev, world, rank):
         line = {"metric": METRIC, "value": pairs * args.steps / max(per_rank), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * max(per_rank) / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"fixed batch of {B} synthetic {nf}-frame 600x800 uint8 clips (seeds 0..{B - 1}) split over "
-                                       f"the ranks ({args.assign}; the reference's nchunks rule drops the remainder), TV-L1 "
+                "config": {"workload": f"fixed batch of {B} synthetic {nf}-frame 600x800 uint8 clips (clip c = seed c % {distinct}) split "
+                                       f"over the ranks ({args.assign}; the reference's nchunks rule drops the remainder), TV-L1 "
                                        "defaults, fp16 flow out, all-gather of per-pair rows",
-                           "clips_per_rank": len(mine), "pairs_total": pairs},
+                           "clips_per_rank": len(mine), "pairs_total": pairs, "distinct_seeds": distinct,
+                           "scheduler_runs_per_step_rank0": info_last.get("scheduler_runs", 1),
+                           "host_seconds_generating_clips_rank0": t_gen},
                 "per_rank_ms_per_step": [1e3 * x / args.steps for x in per_rank],
                 "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / len(per_rank)),
                 "inner_iterations_per_pair_rank0": float(rows.mean())}
@@ -325,6 +364,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="--mode strong: clips in the fixed batch")
     ap.add_argument("--batch-frames", type=int, default=16, help="--mode strong: frames per clip")
     ap.add_argument("--assign", default="contiguous", choices=["contiguous", "roundrobin"])
+    ap.add_argument("--distinct", type=int, default=0, help="--mode strong: distinct clip seeds in the batch (0: all distinct)")
     ap.add_argument("--same-seed", action="store_true", help="weak mode: every rank solves the seed-0 clip")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "teeflow" else args.warmup

@@ -100,7 +100,9 @@ __device__ __forceinline__ void cart_to_polar(float x, float y, float& mag, floa
 }
 
 struct FrameStats {
-    unsigned long long cnt[4];       // non-zero counts: mag, ang, rad, long
+    // non-zero counts: mag, ang, rad, long == lengths of the frame's compacted value lists.  (cnt[0], cnt[1]) and
+    // (cnt[2], cnt[3]) are each bumped by ONE 64-bit atomic (low word = first count; a frame has < 2^28 pixels)
+    unsigned cnt[4];
     unsigned mag_min, mag_max, ang_min, ang_max;          // keys over ALL pixels (np.min / np.max of the arrays)
     unsigned long long rad_min, rad_max, long_min, long_max;
 };
@@ -120,60 +122,82 @@ __global__ void analysis_init_kernel(FrameStats* st, unsigned* ang_hist, int nfr
 
 // masked_arr = vel_array * mask (optical_flow_dataset.py:189-197); mag/ang (analysis.py:232-236);
 // radial unit grid + projections in float64 (analysis.py:89-163).  grid = (chunks, nframes)
+// Every consumer (percentiles, histograms, the angle mode) works on flat[flat != 0] of a frame, so only the NON-ZERO
+// values are kept: frame f's values of a quantity are appended, in no particular order (all consumers are order
+// independent), to the list that starts at element f * npx of its array; stats[f].cnt[] holds the list lengths.
+// One warp-aggregated 64-bit atomic reserves the places of two quantities at once, and warps that see only zeros
+// (outside the mask) touch nothing: the pass writes ~24 bytes per MASKED pixel instead of per pixel.
 __global__ void __launch_bounds__(256)
 analysis_values_kernel(const __half2* __restrict__ flow16, const uint8_t* __restrict__ mask,
                        const double* __restrict__ centroids, int H, int W, float* __restrict__ mag_out,
                        float* __restrict__ ang_out, double* __restrict__ rad_out, double* __restrict__ long_out,
                        FrameStats* __restrict__ stats, unsigned* __restrict__ ang_hist) {
     __shared__ unsigned s_hist[kAngBins];
-    __shared__ unsigned long long s_cnt[4];
     __shared__ unsigned s_k32[4];
     __shared__ unsigned long long s_k64[4];
     const int f = blockIdx.y;
     const int npx = H * W;
     for (int k = threadIdx.x; k < kAngBins; k += blockDim.x) s_hist[k] = 0u;
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) { s_k32[0] = 0xffffffffu; s_k32[1] = 0u; s_k32[2] = 0xffffffffu; s_k32[3] = 0u;
                             s_k64[0] = ~0ull; s_k64[1] = 0ull; s_k64[2] = ~0ull; s_k64[3] = 0ull; }
     __syncthreads();
     const double cH = centroids[2 * f], cW = centroids[2 * f + 1];
     const size_t fo = (size_t)f * npx;
-    unsigned c_mag = 0, c_ang = 0, c_rad = 0, c_long = 0;
+    FrameStats* st = stats + f;
+    unsigned long long* cnt_ma = reinterpret_cast<unsigned long long*>(&st->cnt[0]);
+    unsigned long long* cnt_rl = reinterpret_cast<unsigned long long*>(&st->cnt[2]);
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
     unsigned mag_mn = 0xffffffffu, mag_mx = 0u, ang_mn = 0xffffffffu, ang_mx = 0u;
     unsigned long long rad_mn = ~0ull, rad_mx = 0ull, long_mn = ~0ull, long_mx = 0ull;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
-        const int r = i / W, c = i - r * W;
-        const float2 v = __half22float2(flow16[fo + i]);
-        const uchar2 m = reinterpret_cast<const uchar2*>(mask)[fo + i];
-        const float fx = v.x * (m.x ? 1.f : 0.f), fy = v.y * (m.y ? 1.f : 0.f);
-        float mg, an;
-        cart_to_polar(fx, fy, mg, an);
-        const double v0 = cH - (double)r, v1 = cW - (double)c;
-        const double nrm = sqrt(v0 * v0 + v1 * v1);
-        double u0 = v0 / nrm, u1 = v1 / nrm;
-        if (u0 != u0) u0 = 0.0;                 // np.nan_to_num(vec / norm, nan=0): 0/0 at the centroid
-        if (u1 != u1) u1 = 0.0;
-        const double rad = (double)fx * u0 + (double)fy * u1;
-        const double lng = (double)fx * u1 + (double)fy * (-u0);
-        mag_out[fo + i] = mg; ang_out[fo + i] = an; rad_out[fo + i] = rad; long_out[fo + i] = lng;
-        c_mag += mg != 0.f; c_rad += rad != 0.0; c_long += lng != 0.0;
-        if (an != 0.f) {
-            ++c_ang;
-            const int key = (int)rintf(__fmul_rn(an, 100.f));     // np.round(ang, 2) == rint(ang*100)/100
-            if (key != 0) atomicAdd(&s_hist[min(key, kAngBins - 1)], 1u);
+    for (int i0 = blockIdx.x * blockDim.x; i0 < npx; i0 += gridDim.x * blockDim.x) {    // block-uniform trip count
+        const int i = i0 + (int)threadIdx.x;
+        const bool in = i < npx;
+        float mg = 0.f, an = 0.f;
+        double rad = 0.0, lng = 0.0;
+        if (in) {
+            const int r = i / W, c = i - r * W;
+            const float2 v = __half22float2(flow16[fo + i]);
+            const uchar2 m = reinterpret_cast<const uchar2*>(mask)[fo + i];
+            const float fx = v.x * (m.x ? 1.f : 0.f), fy = v.y * (m.y ? 1.f : 0.f);
+            cart_to_polar(fx, fy, mg, an);
+            const double v0 = cH - (double)r, v1 = cW - (double)c;
+            const double nrm = sqrt(v0 * v0 + v1 * v1);
+            double u0 = v0 / nrm, u1 = v1 / nrm;
+            if (u0 != u0) u0 = 0.0;                 // np.nan_to_num(vec / norm, nan=0): 0/0 at the centroid
+            if (u1 != u1) u1 = 0.0;
+            rad = (double)fx * u0 + (double)fy * u1;
+            lng = (double)fx * u1 + (double)fy * (-u0);
+            if (an != 0.f) {
+                const int key = (int)rintf(__fmul_rn(an, 100.f));     // np.round(ang, 2) == rint(ang*100)/100
+                if (key != 0) atomicAdd(&s_hist[min(key, kAngBins - 1)], 1u);
+            }
+            const unsigned km = f32_key(mg), ka = f32_key(an);
+            mag_mn = min(mag_mn, km); mag_mx = max(mag_mx, km); ang_mn = min(ang_mn, ka); ang_mx = max(ang_mx, ka);
+            const unsigned long long kr = f64_key(rad), kl = f64_key(lng);
+            rad_mn = min(rad_mn, kr); rad_mx = max(rad_mx, kr); long_mn = min(long_mn, kl); long_mx = max(long_mx, kl);
         }
-        const unsigned km = f32_key(mg), ka = f32_key(an);
-        mag_mn = min(mag_mn, km); mag_mx = max(mag_mx, km); ang_mn = min(ang_mn, ka); ang_mx = max(ang_mx, ka);
-        const unsigned long long kr = f64_key(rad), kl = f64_key(lng);
-        rad_mn = min(rad_mn, kr); rad_mx = max(rad_mx, kr); long_mn = min(long_mn, kl); long_mx = max(long_mx, kl);
+        // append the non-zero values to the frame's lists (NaN != 0 is true, like numpy's flat != 0)
+        const bool nz_m = in && mg != 0.f, nz_a = in && an != 0.f, nz_r = in && rad != 0.0, nz_l = in && lng != 0.0;
+        const unsigned bm = __ballot_sync(0xffffffffu, nz_m), ba = __ballot_sync(0xffffffffu, nz_a);
+        const unsigned br = __ballot_sync(0xffffffffu, nz_r), bl = __ballot_sync(0xffffffffu, nz_l);
+        if (bm | ba) {
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(cnt_ma, ((unsigned long long)__popc(ba) << 32) | (unsigned long long)__popc(bm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (nz_m) mag_out[fo + (unsigned)base + __popc(bm & lt)] = mg;
+            if (nz_a) ang_out[fo + (unsigned)(base >> 32) + __popc(ba & lt)] = an;
+        }
+        if (br | bl) {
+            unsigned long long base = 0ull;
+            if (lane == 0) base = atomicAdd(cnt_rl, ((unsigned long long)__popc(bl) << 32) | (unsigned long long)__popc(br));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (nz_r) rad_out[fo + (unsigned)base + __popc(br & lt)] = rad;
+            if (nz_l) long_out[fo + (unsigned)(base >> 32) + __popc(bl & lt)] = lng;
+        }
     }
-    atomicAdd(&s_cnt[0], (unsigned long long)c_mag); atomicAdd(&s_cnt[1], (unsigned long long)c_ang);
-    atomicAdd(&s_cnt[2], (unsigned long long)c_rad); atomicAdd(&s_cnt[3], (unsigned long long)c_long);
     atomicMin(&s_k32[0], mag_mn); atomicMax(&s_k32[1], mag_mx); atomicMin(&s_k32[2], ang_mn); atomicMax(&s_k32[3], ang_mx);
     atomicMin(&s_k64[0], rad_mn); atomicMax(&s_k64[1], rad_mx); atomicMin(&s_k64[2], long_mn); atomicMax(&s_k64[3], long_mx);
     __syncthreads();
-    FrameStats* st = stats + f;
-    if (threadIdx.x < 4) atomicAdd(&st->cnt[threadIdx.x], s_cnt[threadIdx.x]);
     if (threadIdx.x == 0) {
         atomicMin(&st->mag_min, s_k32[0]); atomicMax(&st->mag_max, s_k32[1]);
         atomicMin(&st->ang_min, s_k32[2]); atomicMax(&st->ang_max, s_k32[3]);
@@ -184,13 +208,13 @@ analysis_values_kernel(const __half2* __restrict__ flow16, const uint8_t* __rest
         if (s_hist[k]) atomicAdd(&ang_hist[(size_t)f * kAngBins + k], s_hist[k]);
 }
 
-// Exact order statistics of the NON-ZERO values of one frame by MSB-first radix select (8-bit digits).
+// Exact order statistics of the NON-ZERO values of one frame (its compacted list) by MSB-first radix select (8-bit digits).
 // One CTA per (frame, target group): quantity 0 = mag (float32), 1 = rad, 2 = long (float64); up to 4 target
 // ranks (0-based, among the non-zero values in ascending order; rank < 0 = unused).
 constexpr int kSelTargets = 4;
 __global__ void __launch_bounds__(1024)
 radix_select_kernel(const float* __restrict__ mag, const double* __restrict__ rad, const double* __restrict__ lng,
-                    int npx, const long long* __restrict__ ranks /* [nframes][3][4] */,
+                    int npx, const FrameStats* __restrict__ stats, const long long* __restrict__ ranks /* [nframes][3][4] */,
                     unsigned long long* __restrict__ out_keys /* [nframes][3][4] */) {
     __shared__ unsigned s_hist[kSelTargets][256];
     __shared__ unsigned long long s_prefix[kSelTargets];
@@ -199,6 +223,7 @@ radix_select_kernel(const float* __restrict__ mag, const double* __restrict__ ra
     const bool is64 = qn != 0;
     const int nbits = is64 ? 64 : 32;
     const size_t fo = (size_t)f * npx;
+    const int n = (int)stats[f].cnt[qn == 0 ? 0 : qn + 1];                                     // list length: mag, rad, long
     const unsigned long long zero_pos = is64 ? 0x8000000000000000ull : 0x80000000ull;          // key of +0
     const unsigned long long zero_neg = is64 ? 0x7fffffffffffffffull : 0x7fffffffull;          // key of -0
     if (threadIdx.x < kSelTargets) {
@@ -213,7 +238,7 @@ radix_select_kernel(const float* __restrict__ mag, const double* __restrict__ ra
         bool act[kSelTargets];
 #pragma unroll
         for (int t = 0; t < kSelTargets; ++t) { pre[t] = s_prefix[t]; act[t] = s_rank[t] >= 0; }
-        for (int i = threadIdx.x; i < npx; i += blockDim.x) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
             unsigned long long key;
             if (qn == 0) key = (unsigned long long)f32_key(mag[fo + i]);
             else key = f64_key(qn == 1 ? rad[fo + i] : lng[fo + i]);
@@ -250,7 +275,8 @@ radix_select_kernel(const float* __restrict__ mag, const double* __restrict__ ra
 // T = float (mag, ang) or double (rad, long).  grid = (chunks, nframes)
 template <typename T>
 __global__ void __launch_bounds__(256)
-np_histogram_kernel(const T* __restrict__ vals, int npx, const T* __restrict__ edges, int nbins, T first, T last,
+np_histogram_kernel(const T* __restrict__ vals, int npx, const FrameStats* __restrict__ stats, int quantity,
+                    const T* __restrict__ edges, int nbins, T first, T last,
                     unsigned long long* __restrict__ freq /* [nframes][nbins] */) {
     extern __shared__ unsigned s_bins[];
     const int f = blockIdx.y;
@@ -258,7 +284,8 @@ np_histogram_kernel(const T* __restrict__ vals, int npx, const T* __restrict__ e
     __syncthreads();
     const T denom = last - first;
     const size_t fo = (size_t)f * npx;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += gridDim.x * blockDim.x) {
+    const int n = (int)stats[f].cnt[quantity];       // the frame's list of non-zero values
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const T v = vals[fo + i];
         if (v == (T)0 || !(v >= first) || !(v <= last)) continue;
         const T fi = ((v - first) / denom) * (T)nbins;

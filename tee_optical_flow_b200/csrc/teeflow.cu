@@ -1321,7 +1321,7 @@ int teeflow_analyze_clip(teeflow_handle h, const void* flow_f16_dev, const uint8
         pct_ranks((long long)st[f].cnt[3], perc_hi, false, &r[10], &r[11]);
     }
     CU_TRY(h, cudaMemcpyAsync(h->an_ranks, ranks.data(), sizeof(long long) * ranks.size(), cudaMemcpyHostToDevice, stream));
-    radix_select_kernel<<<dim3(nframes, 3), 1024, 0, stream>>>(h->an_mag, h->an_rad, h->an_long, (int)npx, h->an_ranks, h->an_keys);
+    radix_select_kernel<<<dim3(nframes, 3), 1024, 0, stream>>>(h->an_mag, h->an_rad, h->an_long, (int)npx, h->an_stats, h->an_ranks, h->an_keys);
     CU_TRY(h, cudaGetLastError());
     std::vector<unsigned long long> keys((size_t)nframes * 12);
     CU_TRY(h, cudaMemcpyAsync(keys.data(), h->an_keys, sizeof(unsigned long long) * keys.size(), cudaMemcpyDeviceToHost, stream));
@@ -1374,11 +1374,11 @@ int teeflow_analysis_histogram(teeflow_handle h, int quantity, const void* edges
     const size_t smem = sizeof(unsigned) * nbins;
     if (!f64) {
         const float* e = (const float*)edges_host;
-        np_histogram_kernel<float><<<grid, 256, smem, stream>>>(quantity == 0 ? h->an_mag : h->an_ang, (int)npx,
+        np_histogram_kernel<float><<<grid, 256, smem, stream>>>(quantity == 0 ? h->an_mag : h->an_ang, (int)npx, h->an_stats, quantity,
                                                                 (const float*)h->an_edges, nbins, e[0], e[nbins], h->an_freq);
     } else {
         const double* e = (const double*)edges_host;
-        np_histogram_kernel<double><<<grid, 256, smem, stream>>>(quantity == 2 ? h->an_rad : h->an_long, (int)npx,
+        np_histogram_kernel<double><<<grid, 256, smem, stream>>>(quantity == 2 ? h->an_rad : h->an_long, (int)npx, h->an_stats, quantity,
                                                                  (const double*)h->an_edges, nbins, e[0], e[nbins], h->an_freq);
     }
     CU_TRY(h, cudaGetLastError());

@@ -596,11 +596,14 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     }
     float2 px_c = cur.px, py_c = cur.py;
 
+
     // rows y0 .. y1-2: row y+1 belongs to this strip (u_new stored, error counted); row y+2 <= H is loaded meanwhile.
     // `row` (y+1) is complete when a trip starts; the loads of row y+2 are issued first thing and are first touched
     // by the hand-over `row = nxt` at the END of the trip -- a whole row of work later.  (With the hand-over at the top
     // of the trip ptxas hoisted the new loads above it into scratch registers and copied them home at once: that copy
     // waited for the very load it was meant to hide -- 22 % of all stall samples of the run on one MOV.)
+    // (A loop body of two trips with swapped row buffers -- no hand-over moves, compile-time row parity -- was
+    // measured in round 2: 5.8 % slower on the clip, its larger live set spills inside the loop at 80 registers.)
 #pragma unroll kInnerUnroll
     for (int y = y0; y < y1 - 1; ++y) {
         const bool y_odd = (y & 1) != 0;         // row y + 2 has the parity of y, row y + 1 the other one
@@ -638,7 +641,6 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
             row.px = make_float2(__uint_as_float(__float_as_uint(nxt.px.x) | late), __uint_as_float(__float_as_uint(nxt.px.y) | late));
             row.py = make_float2(__uint_as_float(__float_as_uint(nxt.py.x) | late), __uint_as_float(__float_as_uint(nxt.py.y) | late));
         }
-#endif
         pu += ROWB; pp += ROWB; pc += ROWB;
     }
     // last row of the strip (y = y1-1): u_new of row y1 is only needed for the y-difference (the next strip owns it)
@@ -654,6 +656,7 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
         char* ppw = partner_p(pp);
         if (owner) { st(ppw, 0, pxn); st(ppw, 2 * PB, pyn); }
     }
+#endif
     // fixed-order warp reduction of the float64 error partial
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) err += __shfl_down_sync(0xffffffffu, err, o);

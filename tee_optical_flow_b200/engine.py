@@ -143,6 +143,7 @@ class TVL1Engine:
         code = _dtype_code(I0.dtype)
         H, W = I0.shape
         out = np.empty((H, W, 2), np.float32)
+        self._batch_counters = None
         self._check(self._lib.teeflow_calc_pair_host(self._h, I0.ctypes.data, I1.ctypes.data, code, H, W,
                                                      out.ctypes.data))
         return out
@@ -173,6 +174,7 @@ class TVL1Engine:
         n_out = N - 1 + (1 if duplicate_last else 0)
         f32 = np.empty((n_out, H, W, 2), np.float32) if want_f32 else None
         f16 = np.empty((n_out, H, W, 2), np.float16) if want_f16 else None
+        self._batch_counters = None
         self._check(self._lib.teeflow_calc_clip_host(
             self._h, frames.ctypes.data, code, N, H, W, f32.ctypes.data if want_f32 else None,
             f16.ctypes.data if want_f16 else None, float(np.float32(out_scale)), int(duplicate_last)))
@@ -206,6 +208,7 @@ class TVL1Engine:
         f16 = out_f16 if out_f16 is not None else (
             torch.empty((n_out, H, W, 2), dtype=torch.float16, device=frames.device) if want_f16 else None)
         stream = torch.cuda.current_stream(frames.device).cuda_stream
+        self._batch_counters = None
         entry = self._lib.teeflow_calc_clip_async if asynchronous else self._lib.teeflow_calc_clip
         self._keep = frames                        # an asynchronous run reads the frames after this call returns
         self._check(entry(
@@ -215,9 +218,10 @@ class TVL1Engine:
         return f32, f16
 
     def calc_pairs_device(self, frames, pair_a, pair_b, out_index=None, dup_index=None, n_out=None,
-                          out_scale: float = 1.0, want_f32: bool = True, want_f16: bool = False):
+                          out_scale: float = 1.0, want_f32: bool = True, want_f16: bool = False, out_f32=None, out_f16=None):
         """Generic form: arbitrary (frame a -> frame b) pairs over a CUDA frame tensor (N, H, W); used for
-        batches of clips and for sharding a clip by pair range."""
+        batches of clips and for sharding a clip by pair range.  out_f32 / out_f16: preallocated
+        (n_out, H, W, 2) CUDA tensors to write into instead of allocating."""
         import torch
         pair_a = np.ascontiguousarray(pair_a, np.int32)
         pair_b = np.ascontiguousarray(pair_b, np.int32)
@@ -229,10 +233,16 @@ class TVL1Engine:
         frames = frames.contiguous()
         N, H, W = frames.shape
         code = _lib.TEEFLOW_U8 if frames.dtype == torch.uint8 else _lib.TEEFLOW_F32
-        f32 = torch.empty((n_out, H, W, 2), dtype=torch.float32, device=frames.device) if want_f32 else None
-        f16 = torch.empty((n_out, H, W, 2), dtype=torch.float16, device=frames.device) if want_f16 else None
+        for t, dt in ((out_f32, torch.float32), (out_f16, torch.float16)):
+            if t is not None and (t.dtype != dt or tuple(t.shape) != (n_out, H, W, 2) or not t.is_contiguous() or t.device != frames.device):
+                raise OpticalFlowCalculationError("preallocated output must be a contiguous (n_out, H, W, 2) tensor of the right dtype")
+        f32 = out_f32 if out_f32 is not None else \
+            (torch.empty((n_out, H, W, 2), dtype=torch.float32, device=frames.device) if want_f32 else None)
+        f16 = out_f16 if out_f16 is not None else \
+            (torch.empty((n_out, H, W, 2), dtype=torch.float16, device=frames.device) if want_f16 else None)
         ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
         stream = torch.cuda.current_stream(frames.device).cuda_stream
+        self._batch_counters = None
         self._check(self._lib.teeflow_calc_pairs(
             self._h, frames.data_ptr(), code, N, H, W, H * W, ip(pair_a), ip(pair_b), ip(out_index), ip(dup_index),
             n_pairs, f32.data_ptr() if f32 is not None else None, f16.data_ptr() if f16 is not None else None,
@@ -240,10 +250,12 @@ class TVL1Engine:
         return f32, f16
 
     def calc_batch(self, clips, out_scale: float = 1.0, duplicate_last: bool = True, want_f32: bool = False,
-                   want_f16: bool = True):
-        """A batch of equally shaped clips (B, N, H, W) on one GPU (BASELINE config 4, one rank's share): all
-        B*(N-1) pairs go through ONE scheduler run, so slots freed by one clip are refilled with pairs of the next
-        (no drain between clips).  Returns (f32, f16) shaped (B, N_out, H, W, 2)."""
+                   want_f16: bool = True, max_frames_per_run: int = 1024):
+        """A batch of equally shaped clips (B, N, H, W) on one GPU (BASELINE config 4, one rank's share): the pairs of
+        up to max_frames_per_run frames' worth of clips go through ONE scheduler run, so slots freed by one clip are
+        refilled with pairs of the next (no drain between clips); larger batches are cut into such runs, which bounds
+        the pyramid workspace (~24 MB per 600x800 frame).  Returns (f32, f16) shaped (B, N_out, H, W, 2); the
+        iteration counters of all runs are concatenated in last_counters()."""
         import torch
         if not (isinstance(clips, torch.Tensor) and clips.is_cuda and clips.dim() == 4):
             raise OpticalFlowCalculationError("clips must be a CUDA tensor (B, N, H, W)")
@@ -251,15 +263,30 @@ class TVL1Engine:
         if N < 2:
             raise OpticalFlowCalculationError("a clip needs at least 2 frames")
         n_out = N if duplicate_last else N - 1
-        a = (np.arange(B)[:, None] * N + np.arange(N - 1)[None, :]).ravel().astype(np.int32)
-        o = (np.arange(B)[:, None] * n_out + np.arange(N - 1)[None, :]).ravel().astype(np.int32)
-        d = np.full(B * (N - 1), -1, np.int32)
-        if duplicate_last:
-            d[N - 2::N - 1] = o[N - 2::N - 1] + 1
-        f32, f16 = self.calc_pairs_device(clips.reshape(B * N, H, W), a, a + 1, o, d, n_out=B * n_out,
-                                          out_scale=out_scale, want_f32=want_f32, want_f16=want_f16)
-        rs = lambda t: None if t is None else t.view(B, n_out, H, W, 2)
-        return rs(f32), rs(f16)
+        per_run = max(1, int(max_frames_per_run) // N)
+        f32 = torch.empty((B, n_out, H, W, 2), dtype=torch.float32, device=clips.device) if want_f32 else None
+        f16 = torch.empty((B, n_out, H, W, 2), dtype=torch.float16, device=clips.device) if want_f16 else None
+        counters, infos = [], []
+        for b0 in range(0, B, per_run):
+            b1 = min(b0 + per_run, B)
+            nb = b1 - b0
+            a = (np.arange(nb)[:, None] * N + np.arange(N - 1)[None, :]).ravel().astype(np.int32)
+            o = (np.arange(nb)[:, None] * n_out + np.arange(N - 1)[None, :]).ravel().astype(np.int32)
+            d = np.full(nb * (N - 1), -1, np.int32)
+            if duplicate_last:
+                d[N - 2::N - 1] = o[N - 2::N - 1] + 1
+            self.calc_pairs_device(clips[b0:b1].reshape(nb * N, H, W), a, a + 1, o, d, n_out=nb * n_out, out_scale=out_scale,
+                                   want_f32=want_f32, want_f16=want_f16,
+                                   out_f32=None if f32 is None else f32[b0:b1].view(nb * n_out, H, W, 2),
+                                   out_f16=None if f16 is None else f16[b0:b1].view(nb * n_out, H, W, 2))
+            if B > per_run:
+                c, info = self.last_counters()
+                counters.append(c); infos.append(info)
+        if counters:
+            self._batch_counters = (np.concatenate(counters, axis=0), infos)
+        else:
+            self._batch_counters = None
+        return f32, f16
 
     # ------------------------------------------------------------------ frame prep
     def prepare_frames(self, rgb):
@@ -393,6 +420,15 @@ class TVL1Engine:
     def last_counters(self) -> Tuple[np.ndarray, dict]:
         """(counters[n_pairs, n_levels, 3] = inner iterations / median passes / warps executed per level,
         info dict) of the last calc -- the inputs of the roofline accounting."""
+        bc = getattr(self, "_batch_counters", None)
+        if bc is not None:              # a calc_batch that was cut into several scheduler runs: counters of all of them
+            c, infos = bc
+            info = dict(infos[-1])
+            for k in ("n_pairs", "device_ms", "pyramid_ms", "solver_ms", "solver_launches", "kernel_launches",
+                      "double_steps", "double_steps_discarded"):
+                info[k] = sum(i[k] for i in infos)
+            info["scheduler_runs"] = len(infos)
+            return c, info
         st = _lib.TeeflowStats()
         self._check(self._lib.teeflow_get_stats(self._h, C.byref(st)))
         n = st.n_pairs
