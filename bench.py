@@ -303,9 +303,12 @@ def strong_scaling(args, eng, dev, world, rank):
     out16 = None
     info_last = {}
 
+    compute_ms = 0.0
+
     def step():
-        nonlocal out16
-        _, out16 = eng.calc_batch(d, want_f32=False, want_f16=True)
+        nonlocal out16, compute_ms
+        _, out16 = eng.calc_batch(d, want_f32=False, want_f16=True)     # synchronises: the rank's own share is done here
+        compute_ms += eng.last_counters()[1]["device_ms"]
         nonlocal info_last
         counters, info_last = eng.last_counters()
         rows = counters[:, :, 0].sum(axis=1, keepdims=True).astype(np.float64)       # inner iterations per pair
@@ -322,18 +325,20 @@ def strong_scaling(args, eng, dev, world, rank):
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    compute_ms = 0.0
     for _ in range(args.steps):
         rows = step()
     ev1.record()
     torch.cuda.synchronize()
     mine_s = ev0.elapsed_time(ev1) / 1e3
-    t = torch.tensor([mine_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([mine_s, compute_ms / 1e3], dtype=torch.float64, device=dev)
     allt = [torch.zeros_like(t) for _ in range(world)]
     if world > 1:
         dist.all_gather(allt, t)
     else:
         allt = [t]
-    per_rank = [float(x.item()) for x in allt]
+    per_rank = [float(x[0].item()) for x in allt]
+    per_rank_compute = [float(x[1].item()) for x in allt]   # device time of the rank's own share, before the collective
     if rank == 0:
         pairs = (B - B % world) * (nf - 1)
         line = {"metric": METRIC, "value": pairs * args.steps / max(per_rank), "unit": UNIT, "n_gpus": world,
@@ -346,7 +351,9 @@ def strong_scaling(args, eng, dev, world, rank):
                            "scheduler_runs_per_step_rank0": info_last.get("scheduler_runs", 1),
                            "host_seconds_generating_clips_rank0": t_gen},
                 "per_rank_ms_per_step": [1e3 * x / args.steps for x in per_rank],
-                "imbalance_max_over_mean": max(per_rank) / (sum(per_rank) / len(per_rank)),
+                "per_rank_compute_ms_per_step": [1e3 * x / args.steps for x in per_rank_compute],
+                "imbalance_max_over_mean": max(per_rank_compute) / (sum(per_rank_compute) / len(per_rank_compute)),
+                "imbalance_what": "device time of each rank's own share (the all-gather that follows equalises the step times)",
                 "inner_iterations_per_pair_rank0": float(rows.mean())}
         print(json.dumps(line), flush=True)
 
