@@ -17,6 +17,10 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libteeflow.so"
+# second build of the same translation unit with the TMA-staged inner iteration (-DTEEFLOW_TMA_INNER=1): bit-identical
+# results, slower; kept building and parity-tested (tests/test_tma_variant_gpu.py, TEEFLOW_LIB selects it)
+LIB_TMA = PKG / "libteeflow_tma.so"
+VARIANTS = {None: (LIB, []), "tma": (LIB_TMA, ["-DTEEFLOW_TMA_INNER=1"])}
 SOURCES = [CSRC / "teeflow.cu"]
 # every header the translation unit can include: a stale library after an edit would go unnoticed by the tests
 HEADERS = sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc")) + sorted(CSRC.glob("*.h")) + \
@@ -37,19 +41,21 @@ def find_nvcc() -> str:
     raise RuntimeError("nvcc not found (set $NVCC)")
 
 
-def needs_build() -> bool:
-    if not LIB.exists():
+def needs_build(variant=None) -> bool:
+    lib = VARIANTS[variant][0]
+    if not lib.exists():
         return True
-    t = LIB.stat().st_mtime
+    t = lib.stat().st_mtime
     return any(p.exists() and p.stat().st_mtime > t for p in SOURCES + HEADERS + [Path(__file__)])
 
 
-def build_library(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
-        return LIB
-    # TEEFLOW_NVCC_EXTRA: extra flags for tuning experiments (e.g. "-DTEEFLOW_MIN_CTAS=3 -DTEEFLOW_RING=2")
+def build_library(force: bool = False, verbose: bool = False, variant=None) -> Path:
+    lib, defines = VARIANTS[variant]
+    if not force and not needs_build(variant):
+        return lib
+    # TEEFLOW_NVCC_EXTRA: extra flags for tuning experiments (e.g. "-DTEEFLOW_MIN_CTAS=3 -DTEEFLOW_PF_ROWS=6")
     extra = os.environ.get("TEEFLOW_NVCC_EXTRA", "").split()
-    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", str(LIB), *map(str, SOURCES)]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *defines, *extra, "-o", str(lib), *map(str, SOURCES)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)
@@ -60,8 +66,10 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
         print(res.stdout, file=sys.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout[-4000:]}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
+    if "--all" in sys.argv:
+        print(build_library(force="--force" in sys.argv, verbose=True, variant="tma"))

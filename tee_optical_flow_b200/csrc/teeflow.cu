@@ -66,6 +66,7 @@ struct teeflow_engine {
     int pending = 0;                  // an asynchronous dataflow run is in flight: teeflow_finish() completes it
     int pending_pairs = 0, pending_grid = 0;
     cudaStream_t pending_stream = nullptr;
+    CUtensorMap* tmaps = nullptr;     // [kMaxLevels][3] device copies of the tensor maps over the slot planes (TMA staging)
     Task* tasks = nullptr;            // [kTaskRing] task descriptors of the dataflow scheduler
     FlowCtl* flow_ctl = nullptr;
     unsigned long long* flow_stats = nullptr;   // [32] device, diagnostic builds
@@ -267,7 +268,7 @@ int teeflow_destroy(teeflow_handle h) {
     if (h->pending) { cudaStreamSynchronize(h->pending_stream); h->pending = 0; }
     cudaFree(h->pyrI); cudaFree(h->pyrG);
     cudaFree(h->planes_raw); cudaFree(h->slots); cudaFree(h->arrive); cudaFree(h->partial); cudaFree(h->ctl);
-    cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg); cudaFree(h->tasks); cudaFree(h->flow_ctl); cudaFree(h->flow_stats);
+    cudaFree(h->pair_lists); cudaFree(h->counters); cudaFree(h->bg); cudaFree(h->tasks); cudaFree(h->flow_ctl); cudaFree(h->flow_stats); cudaFree(h->tmaps);
     if (h->h_flow_order) cudaFreeHost(h->h_flow_order);
     cudaFree(h->an_mag); cudaFree(h->an_ang); cudaFree(h->an_rad); cudaFree(h->an_long); cudaFree(h->an_cent);
     cudaFree(h->an_stats); cudaFree(h->an_anghist); cudaFree(h->an_ranks); cudaFree(h->an_keys);
@@ -524,6 +525,60 @@ static int ensure_workspace(teeflow_engine* h, size_t n_frames, size_t pyr_strid
 
 // host_f32 / host_f16 (optional): host mirrors of the output buffers; the flow of a finished pair is copied out while
 // the other pairs are still being solved (a frame pair is an independent unit, its result is final once written)
+// ---- tensor maps of the TMA-staged inner iteration (op_inner_tma): per pyramid level three 4-D maps over the slot
+// planes, dimensions (column, plane, row, slot) in 8-byte elements; elements outside a level's W x H read as zero.
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+    static tmap_encode_fn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (tmap_encode_fn)p;
+    }
+    return fn;
+}
+
+static int build_tensor_maps(teeflow_engine* h, const EngineParams& P, int pitch, int n_slots, CUtensorMap* maps /* [L][3] */) {
+    tmap_encode_fn enc = tmap_encoder();
+    if (!enc) return fail(h, TEEFLOW_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t PB = (cuuint64_t)pitch * 8u, ROWB = PB * kPlanes, SLOTB = (cuuint64_t)P.slot_stride * 8u;
+    const cuuint32_t ones[4] = {1, 1, 1, 1};
+    for (int l = 0; l < P.L; ++l) {
+        const cuuint64_t Wl = (cuuint64_t)P.lv[l].W, Hl = (cuuint64_t)P.lv[l].H;
+        CUresult r;
+        {   // [0] one plane, 34 columns x kTR rows (U[ucur], CA)
+            const cuuint64_t dims[4] = {Wl, (cuuint64_t)kPlanes, Hl, (cuuint64_t)n_slots};
+            const cuuint64_t strides[3] = {PB, ROWB, SLOTB};
+            const cuuint32_t box[4] = {(cuuint32_t)kTBW, 1, (cuuint32_t)kTR, 1};
+            r = enc(&maps[l * 3 + 0], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)P.planes, dims, strides, box, ones,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(h, TEEFLOW_ERR_CUDA, "cuTensorMapEncodeTiled (plane box, level %d) failed: %d", l, (int)r);
+            // [1] PX[pcur] and PY[pcur] (two planes apart: plane step 2), 34 columns, kTR rows
+            const cuuint32_t boxp[4] = {(cuuint32_t)kTBW, 4, (cuuint32_t)kTR, 1};
+            const cuuint32_t stepp[4] = {1, 2, 1, 1};
+            r = enc(&maps[l * 3 + 1], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)P.planes, dims, strides, boxp, stepp,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(h, TEEFLOW_ERR_CUDA, "cuTensorMapEncodeTiled (dual box, level %d) failed: %d", l, (int)r);
+        }
+        {   // [2] the CB plane of the even image rows: (rho_c(y), rho_c(y + 1)) per element, 34 columns x kTR/2 row pairs
+            const cuuint64_t dims[4] = {Wl, 1, (Hl + 1) / 2, (cuuint64_t)n_slots};
+            const cuuint64_t strides[3] = {PB, 2 * ROWB, SLOTB};
+            const cuuint32_t box[4] = {(cuuint32_t)kTBW, 1, (cuuint32_t)(kTR / 2), 1};
+            r = enc(&maps[l * 3 + 2], CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, (void*)(P.planes + (size_t)PL_CB * pitch), dims, strides, box,
+                    ones, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(h, TEEFLOW_ERR_CUDA, "cuTensorMapEncodeTiled (rho_c box, level %d) failed: %d", l, (int)r);
+        }
+    }
+    return TEEFLOW_OK;
+}
+
 static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, int n_frames, int H, int W,
                           int64_t frame_stride, const int32_t* pair_a, const int32_t* pair_b, const int32_t* out_index,
                           const int32_t* dup_index, int n_pairs, float* flow_f32_dev, void* flow_f16_dev, float out_scale,
@@ -628,6 +683,14 @@ static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, 
     P.bg_out = h->bg;
     P.flow_f32 = (float2*)flow_f32_dev;
     P.flow_f16 = (uint32_t*)flow_f16_dev;
+    alignas(64) CUtensorMap tmaps_host[kMaxLevels * 3];   // host temporary: copied before the first stream synchronisation below
+    if (kTma) {
+        rc = build_tensor_maps(h, P, pitch, S, tmaps_host);
+        if (rc) return rc;
+        if (!h->tmaps) CU_TRY(h, cudaMalloc(&h->tmaps, sizeof(CUtensorMap) * kMaxLevels * 3));
+        CU_TRY(h, cudaMemcpyAsync(h->tmaps, tmaps_host, sizeof(CUtensorMap) * 3 * L, cudaMemcpyHostToDevice, stream));
+        P.tmaps = h->tmaps;
+    }
 
     CU_TRY(h, cudaEventRecord(h->ev_t0, stream));
     CU_TRY(h, cudaMemsetAsync(h->bg, 0, sizeof(float) * n_pairs, stream));
@@ -783,6 +846,7 @@ static int run_pairs_impl(teeflow_engine* h, const void* frames_dev, int dtype, 
         CU_TRY(h, cudaMemcpy(&c1, h->flow_ctl, sizeof(c1), cudaMemcpyDeviceToHost));
         CU_TRY(h, cudaMemcpy(h->flow_stats_host, h->flow_stats, sizeof(h->flow_stats_host), cudaMemcpyDeviceToHost));
         if (c1.abort) return fail(h, TEEFLOW_ERR_STATE, c1.abort == 1 ? "dataflow scheduler watchdog: a warp waited too long for a task"
+                                                       : c1.abort == 3 ? "a warp waited too long for a TMA box of the inner iteration"
                                                                        : "dataflow scheduler lost the task ring");
         if (c1.pairs_done < n_pairs) return fail(h, TEEFLOW_ERR_STATE, "scheduler stopped with %d of %d pairs done", c1.pairs_done, n_pairs);
         if (copy_out) {

@@ -65,6 +65,85 @@ constexpr int kPF = TEEFLOW_PF_ROWS;   // inner iteration: rows ahead of the cur
 constexpr bool kRhoPack = TEEFLOW_RHO_PACK != 0;
 static_assert(!kRhoPack || (kIR % 2 == 0 && kIR2 % 2 == 0 && kPR % 2 == 0), "row-pair packing of rho_c needs even strip heights");
 
+// ---- TMA staging of the inner iteration's input rows (op_inner_tma)
+// 0 (shipped default): the inner iteration reads its rows through registers one row ahead + L2 prefetches (op_inner).
+// 1 (libteeflow_tma.so, built and parity-tested next to the default): TMA-staged rows (op_inner_tma); bit-identical,
+// measured 10-12 % slower on the clip in every ring geometry (profiles/r2_summary.md).
+#ifndef TEEFLOW_TMA_INNER
+#define TEEFLOW_TMA_INNER 0
+#endif
+#ifndef TEEFLOW_TMA_ROWS
+#define TEEFLOW_TMA_ROWS 2
+#endif
+#ifndef TEEFLOW_TMA_STAGES
+#define TEEFLOW_TMA_STAGES 2
+#endif
+constexpr bool kTma = TEEFLOW_TMA_INNER != 0;
+constexpr int kTR = TEEFLOW_TMA_ROWS;      // image rows per box (one chunk of a strip)
+constexpr int kTS = TEEFLOW_TMA_STAGES;    // chunks in flight per warp (ring depth)
+static_assert(!kTma || (kRhoPack && kTR % 2 == 0 && kTR >= 2 && kTS >= 2 && kTS <= 8), "TMA ring geometry");
+// The first coordinate of a box must be a multiple of 16 bytes = two 8-byte elements (an odd one faults: measured,
+// tools/tma_probe2.cu), and strips start every 31 columns: every box is 34 columns wide and starts on the even column
+// at or below the first column it needs; the lanes read at an offset of 0 or 1 elements.
+constexpr int kTBW = 34;
+constexpr unsigned round128(unsigned v) { return (v + 127u) & ~127u; }
+constexpr unsigned kTRowB = (unsigned)kTBW * 8u;            // bytes of one staged plane row
+constexpr unsigned kTOffU = 0u;
+constexpr unsigned kTOffCA = round128(kTOffU + kTR * kTRowB);
+constexpr unsigned kTOffP = round128(kTOffCA + kTR * kTRowB);    // box layout: [row][PX, PY][34 columns]
+constexpr unsigned kTOffCB = round128(kTOffP + kTR * 2u * kTRowB);
+constexpr unsigned kTStageB = round128(kTOffCB + (kTR / 2) * kTRowB);
+constexpr unsigned kTTxBytes = 2u * kTR * kTRowB + kTR * 2u * kTRowB + (kTR / 2) * kTRowB;   // bytes one chunk delivers
+constexpr unsigned kTWarpB = kTS * kTStageB;
+
+struct TmaRing {              // one warp's staging ring (shared memory)
+    uint32_t ring;            // shared-memory address of its kTS stages
+    uint32_t mbar;            // ... of its kTS mbarriers (8 bytes each)
+    unsigned* phase;          // parity bits of the mbarriers: persist from strip to strip
+};
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// One chunk of a strip: arm the stage's mbarrier and ask for its four boxes.  Executed by the WHOLE warp with identical
+// operands; one elected lane issues (in a divergent `if (lane == 0)` ptxas wraps every UTMALDG in a waterfall loop
+// of eight R2UR broadcasts -- 78 instructions per chunk; here the warp-uniform operands are moved once).
+__device__ __forceinline__ void tma_issue_chunk(uint32_t dst, uint32_t bar, const CUtensorMap* tm, int xe, int xp, int plane_u,
+                                                int plane_px, int row, int slot) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 d1, d2, d3, r2;\n\t"
+        ".reg .b64 t1, t2;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "add.u32 d1, %0, %9;\n\t"
+        "add.u32 d2, %0, %10;\n\t"
+        "add.u32 d3, %0, %11;\n\t"
+        "add.u64 t1, %2, 128;\n\t"
+        "add.u64 t2, %2, 256;\n\t"
+        "shr.s32 r2, %7, 1;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %12;\n\t"
+        "@p cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%2, {%3, %5, %7, %8}], [%1];\n\t"
+        "@p cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [d1], [%2, {%3, %13, %7, %8}], [%1];\n\t"
+        "@p cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [d2], [t1, {%4, %6, %7, %8}], [%1];\n\t"
+        "@p cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [d3], [t2, {%3, %14, r2, %8}], [%1];\n\t"
+        "}"
+        ::"r"(dst), "r"(bar), "l"(tm), "r"(xe), "r"(xp), "r"(plane_u), "r"(plane_px), "r"(row), "r"(slot), "n"(kTOffCA),
+          "n"(kTOffP), "n"(kTOffCB), "n"(kTTxBytes), "n"((int)PL_CA), "n"(0)
+        : "memory");
+}
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------ pyramid
 // level 0: convertTo(CV_32F, 1) for u8, x255 for f32 (tvl1flow.cpp: I0mult / I1mult)
 __global__ void pyr_level0_kernel(const void* __restrict__ frames, int dtype, long long frame_stride, int n_frames,
@@ -663,6 +742,161 @@ __device__ __forceinline__ double op_inner(const EngineParams& P, int level, int
     return err;
 }
 
+// PH_INNER, TMA-staged form (the shipped one when TEEFLOW_TMA_INNER): the same iteration, the same strip geometry and
+// the same arithmetic in the same order as op_inner, but the input rows do not travel through registers one row
+// ahead: lane 0 asks the TMA unit for boxes of kTR image rows (cp.async.bulk.tensor through the tensor maps of the
+// level: U, CA, PX + PY in one box (from column x0-1, so every lane finds its left neighbour's px next to its own, and
+// the column left of the image reads as zero) and the row-pair packed rho_c, all 34 columns wide), kTS boxes deep into the warp's shared-memory ring, each signalled by an mbarrier; the lanes pick their
+// values up with 8-byte shared loads when the trip needs them.  Up to kTS * kTR rows per warp are in flight without a
+// register, which is what the register form could not afford (its first use of the next row's loads held 9 % of the
+// kernel's stall samples).  Columns >= W and the row below the image are out of bounds of the tensor map and read as
+// zero: they take no exact-form branch and are never stored.  Stores go straight from registers to the partner planes.
+template <int PITCH>
+__device__ __forceinline__ double op_inner_tma(const EngineParams& P, int level, int ucur, int pcur, int slot, int strip,
+                                               int lane, const TmaRing& T) {
+    using L = Lay<PITCH>;
+    constexpr int PB = (int)L::PB, ROWB = (int)L::ROWB;
+    const LevelGeom& g = P.lv[level];
+    const int W = g.W, H = g.H;
+    const InnerConst K = {P.l_t, P.theta, P.taut, P.negzero};
+
+    const int x0 = (strip % g.in_sx) * kIW;
+    const int y0 = (strip / g.in_sx) * kIR, y1 = min(y0 + kIR, H);
+    const int x = x0 + lane;
+    const bool valid = x < W;
+    const bool owner = valid && lane < kIW;      // lane owns the outputs of its column
+    const unsigned right_mask = (x + 1 < W) ? 0xffffffffu : 0u;   // forward x-difference exists
+    const bool strip_at_x0 = (x0 == 0);          // warp-uniform
+    const bool first_col = (x == 0);
+    const int xc = valid ? x : W - 1;            // idle lanes: a legal address (they never store)
+    char* gbase = reinterpret_cast<char*>(slot_base(P, slot)) + ((size_t)y0 * (size_t)ROWB + (size_t)(xc + kXMargin) * 8u);
+    char* gu = gbase + (ucur ^ 1) * PB;                     // partner U of row y0 (results)
+    char* gp = gbase + ((int)PL_PX + (pcur ^ 1)) * PB;      // partner PX; partner PY at + 2 PB
+    auto st = [](char* p, int off, float2 v) { *reinterpret_cast<float2*>(p + off) = v; };
+
+    // input rows y0 .. y1 (row y1 only for the y-difference of the last row; none below the image)
+    const int n_in = (y1 - y0) + (y1 < H ? 1 : 0);
+    const int n_chunks = (n_in + kTR - 1) / kTR;
+    const CUtensorMap* tm = P.tmaps + level * 3;
+    const int xe = x0 & ~1, xp = (x0 - 1) & ~1;              // even first columns of the boxes (xp = -2 for the first strip)
+    const unsigned lo = (unsigned)(x0 - xe + lane) * 8u;     // byte offset of this lane's column in a staged U / CA / rho_c row
+    const unsigned lp = (unsigned)(x0 - 1 - xp + lane) * 8u; // ... of its LEFT neighbour's column in a staged PX / PY row
+    unsigned ph = *T.phase;
+    auto issue = [&](int c, int stage) {         // whole warp, convergent: chunk c = rows y0 + c kTR ... into `stage`
+        tma_issue_chunk(T.ring + (unsigned)stage * kTStageB, T.mbar + (unsigned)stage * 8u, tm, xe, xp, ucur, (int)PL_PX + pcur,
+                        y0 + c * kTR, slot);
+    };
+    // the planes were written by other SMs' ordinary stores (made visible before the task was published): order them
+    // before the reads through the async proxy
+    asm volatile("fence.proxy.async;" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < kTS; ++c) if (c < n_chunks) issue(c, c);
+    float2 pyu = make_float2(0.f, 0.f);          // py of the row above the strip: one direct load
+    if (y0 > 0) pyu = __ldcg(reinterpret_cast<const float2*>(gbase + ((int)PL_PY + pcur) * PB - ROWB));
+
+    int k = 0, rr = 0, stage = 0, c_next = kTS;
+    bool timed_out = false;
+    auto fetch = [&]() {                         // the next input row of the strip, from the ring
+        if (rr == 0) {
+            const uint32_t bar = T.mbar + (unsigned)stage * 8u;
+            const uint32_t parity = (ph >> stage) & 1u;
+            if (!mbar_try_wait(bar, parity)) {
+                const long long t0 = clock64();
+                unsigned spins = 0;
+                while (!mbar_try_wait(bar, parity)) {
+                    if ((++spins & 0x3ffu) == 0u) {
+                        const bool dead = P.flow && *reinterpret_cast<volatile int*>(&P.flow->abort) != 0;
+                        if (dead || clock64() - t0 > P.watchdog_cycles) {
+                            if (P.flow && !dead) atomicExch(&P.flow->abort, 3);
+                            timed_out = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            ph ^= 1u << stage;
+        }
+        const uint32_t sb = T.ring + (unsigned)stage * kTStageB;
+        const uint32_t a = sb + (unsigned)rr * kTRowB + lo;
+        const uint32_t ap = sb + kTOffP + (unsigned)rr * (2u * kTRowB) + lp;
+        InnerRow r;
+        r.u = lds64(a + kTOffU);
+        r.ca = lds64(a + kTOffCA);
+        r.pxl = lds64(ap);                       // px of column x - 1 (zero left of the image)
+        r.px = lds64(ap + 8u);
+        r.py = lds64(ap + kTRowB + 8u);
+        r.cb = lds64(sb + kTOffCB + (unsigned)(rr >> 1) * kTRowB + lo);   // (rho_c even row, rho_c odd row)
+        ++k; ++rr;
+        if (rr == kTR || k == n_in) {            // every lane has its values of this stage: hand it back to the TMA unit
+            __syncwarp();
+            if (c_next < n_chunks) issue(c_next, stage);
+            ++c_next; rr = 0;
+            stage = (stage + 1 == kTS) ? 0 : stage + 1;
+        }
+        return r;
+    };
+    auto diff_x = [&](float2 un) {               // forward x-difference of u_new (zero in the last image column)
+        const float2 d = sub2(make_float2(__shfl_down_sync(0xffffffffu, un.x, 1), __shfl_down_sync(0xffffffffu, un.y, 1)), un);
+        return make_float2(and_mask(d.x, right_mask), and_mask(d.y, right_mask));
+    };
+
+    double err = 0.0;
+    const InnerRow cur = fetch();                // row y0 (even: kIR is)
+    float2 un = estimate_u_px(cur, cur.pxl, pyu, strip_at_x0, first_col && y0 > 0, K, false);
+    if (owner) {
+        st(gu, 0, un);
+        const float2 du = sub2(un, cur.u);
+        const float2 sq = mul2(du, du);
+        err += (double)(sq.x + sq.y);
+    }
+    float2 px_c = cur.px, py_c = cur.py;
+#pragma unroll 1
+    for (int y = y0; y < y1 - 1; ++y) {
+        const InnerRow row = fetch();            // row y + 1
+        // u_new of row y+1, then forwardGradient(u_new) + estimateDualVariables of row y -- fast forms
+        VStep v = estimate_v_fast(row, K, (y & 1) == 0);
+        const float2 tdv = theta_div_px(row, row.pxl, py_c, strip_at_x0, first_col, K);
+        float2 un_n = add2(add2(row.u, v.d), tdv);
+        const float2 ux = diff_x(un);
+        float2 pxn, pyn;
+        const bool ok = dual_update_fast(ux, sub2(un_n, un), px_c, py_c, K, pxn, pyn);
+        if (v.bad || !ok) {                      // rare: redo this lane's row with the exact forms
+            if (v.bad) un_n = add2(add2(row.u, estimate_v_exact(row, v)), tdv);
+            dual_update_exact(ux, sub2(un_n, un), px_c, py_c, K, pxn, pyn);
+        }
+        if (owner) {
+            st(gu, ROWB, un_n);
+            st(gp, 0, pxn);
+            st(gp, 2 * PB, pyn);
+            const float2 du = sub2(un_n, row.u);
+            const float2 sq = mul2(du, du);
+            err += (double)(sq.x + sq.y);
+        }
+        un = un_n; px_c = row.px; py_c = row.py;
+        gu += ROWB; gp += ROWB;
+    }
+    // last row of the strip (y = y1-1): u_new of row y1 is only needed for the y-difference (the next strip owns it)
+    {
+        float2 uy = make_float2(0.f, 0.f);
+        if (y1 < H) {                            // warp-uniform
+            const InnerRow row = fetch();
+            const float2 un_n = estimate_u_px(row, row.pxl, py_c, strip_at_x0, first_col, K, (y1 & 1) != 0);
+            uy = sub2(un_n, un);
+        }
+        const float2 ux = diff_x(un);
+        float2 pxn, pyn;
+        if (!dual_update_fast(ux, uy, px_c, py_c, K, pxn, pyn)) dual_update_exact(ux, uy, px_c, py_c, K, pxn, pyn);
+        if (owner) { st(gp, 0, pxn); st(gp, 2 * PB, pyn); }
+    }
+    if (lane == 0) *T.phase = ph;
+    __syncwarp();
+    if (timed_out) err = __longlong_as_double(0x7ff8000000000000ll);   // the run is aborted; make the damage visible
+    // fixed-order warp reduction of the float64 error partial
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err += __shfl_down_sync(0xffffffffu, err, o);
+    return err;
+}
+
 // PH_INNER2: TWO primal-dual iterations in one pass over the state (temporal blocking): 40 bytes read and 24
 // written per pixel for two iterations instead of one.  Register-only: a warp owns kIW2 = 29 output columns and kIR2
 // rows; its 32 lanes sit on columns x0-1 .. x0+30 and it walks rows y0-1 .. y1+1, a four-stage software pipeline
@@ -910,12 +1144,15 @@ __device__ __forceinline__ constexpr bool has_op(int phase) { return ((TEEFLOW_P
 
 template <int PITCH>
 __device__ __forceinline__ void run_strip(const EngineParams& P, int phase, int level, int ucur, int pcur, int pair,
-                                          float bg, int slot, int strip, int lane, const float4* s_cubic, double& err,
-                                          double& aux) {
+                                          float bg, int slot, int strip, int lane, const float4* s_cubic, const TmaRing& T,
+                                          double& err, double& aux) {
     if (has_op(PH_LEVEL_INIT) && phase == PH_LEVEL_INIT) op_level_init<PITCH>(P, level, ucur, slot, strip, lane);
     else if (has_op(PH_WARP) && phase == PH_WARP) op_warp<PITCH>(P, level, ucur, pair, slot, strip, lane, s_cubic);
     else if (has_op(PH_MEDIAN) && phase == PH_MEDIAN) op_median<PITCH>(P, level, ucur, slot, strip, lane);
-    else if (has_op(PH_INNER) && phase == PH_INNER) err = op_inner<PITCH>(P, level, ucur, pcur, slot, strip, lane);
+    else if (has_op(PH_INNER) && phase == PH_INNER) {
+        if constexpr (kTma) err = op_inner_tma<PITCH>(P, level, ucur, pcur, slot, strip, lane, T);
+        else err = op_inner<PITCH>(P, level, ucur, pcur, slot, strip, lane);
+    }
     else if (has_op(PH_INNER2) && phase == PH_INNER2) op_inner2<PITCH>(P, level, ucur, pcur, slot, strip, lane, err, aux);
     else if (has_op(PH_WASE) && phase == PH_WASE) op_wase<PITCH>(P, ucur, slot, strip, lane, err, aux);
     else if (has_op(PH_FINAL) && phase == PH_FINAL) op_final<PITCH>(P, ucur, pair, bg, slot, strip, lane);
@@ -991,6 +1228,17 @@ __global__ void __launch_bounds__(kThreads, TEEFLOW_MIN_CTAS)
 tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
     __shared__ int s_prefix[kMaxSlots + 1];
     __shared__ float4 s_cubic[32];
+    // TMA staging ring of the inner iteration: kTS stages and mbarriers per warp (op_inner_tma)
+    __shared__ __align__(128) unsigned char s_ring[kTma ? kWarpsPerCta * kTWarpB : 16];
+    __shared__ __align__(8) unsigned long long s_mbar[kWarpsPerCta * kTS];
+    __shared__ unsigned s_tphase[kWarpsPerCta];
+    if (kTma) {
+        if (threadIdx.x < kWarpsPerCta * kTS) mbar_init(smem_u32(&s_mbar[threadIdx.x]), 1u);
+        if (threadIdx.x < kWarpsPerCta) s_tphase[threadIdx.x] = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const TmaRing T = {smem_u32(s_ring) + (threadIdx.x >> 5) * kTWarpB, smem_u32(s_mbar) + (threadIdx.x >> 5) * (kTS * 8u),
+                       &s_tphase[threadIdx.x >> 5]};
 
     // this launch serves the slot group [slot0, slot0 + S): groups run on separate streams so that the tail and
     // the launch gap of one group's step are filled by the other group's strips
@@ -1036,7 +1284,7 @@ tvl1_step_kernel(const __grid_constant__ EngineParams P, const int parity) {
         const int n_items = s_prefix[lo + 1] - s_prefix[lo];
 
         double err = 0.0, aux = 0.0;
-        run_strip<PITCH>(P, phase, level, ucur, pcur, pair, sp->bg, slot, strip, lane, s_cubic, err, aux);
+        run_strip<PITCH>(P, phase, level, ucur, pcur, pair, sp->bg, slot, strip, lane, s_cubic, T, err, aux);
         __syncwarp();
         if (strip_arrive(P, phase, slot, strip, n_items, lane, err, aux)) {
             // last strip of this slot for this step: reduce the partials in strip order and advance the slot
@@ -1119,6 +1367,17 @@ template <int PITCH>
 __global__ void __launch_bounds__(kThreads, TEEFLOW_MIN_CTAS)
 tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
     __shared__ float4 s_cubic[32];
+    // TMA staging ring of the inner iteration: kTS stages and mbarriers per warp (op_inner_tma)
+    __shared__ __align__(128) unsigned char s_ring[kTma ? kWarpsPerCta * kTWarpB : 16];
+    __shared__ __align__(8) unsigned long long s_mbar[kWarpsPerCta * kTS];
+    __shared__ unsigned s_tphase[kWarpsPerCta];
+    if (kTma) {
+        if (threadIdx.x < kWarpsPerCta * kTS) mbar_init(smem_u32(&s_mbar[threadIdx.x]), 1u);
+        if (threadIdx.x < kWarpsPerCta) s_tphase[threadIdx.x] = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const TmaRing T = {smem_u32(s_ring) + (threadIdx.x >> 5) * kTWarpB, smem_u32(s_mbar) + (threadIdx.x >> 5) * (kTS * 8u),
+                       &s_tphase[threadIdx.x >> 5]};
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < 32) s_cubic[tid] = cubic_coeffs(tid);
     __syncthreads();
@@ -1225,7 +1484,7 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
         TF_STAT(10)
 
         double err = 0.0, aux = 0.0;
-        run_strip<PITCH>(P, phase, level, ucur, pcur, pair, bg, slot, strip, lane, s_cubic, err, aux);
+        run_strip<PITCH>(P, phase, level, ucur, pcur, pair, bg, slot, strip, lane, s_cubic, T, err, aux);
         __syncwarp();
         TF_STAT(phase)
 #if TEEFLOW_EARLY_PROBE

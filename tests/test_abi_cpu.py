@@ -113,3 +113,21 @@ def test_median_networks_are_verified_and_current():
                          capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "wrong medians over 2^25 zero-one windows: 0" in res.stdout
+
+
+def test_tma_variant_builds_exports_the_abi_and_carries_tma_instructions(built_lib):
+    """libteeflow_tma.so (same source, -DTEEFLOW_TMA_INNER=1) builds, exports every declared symbol, and its SASS holds
+    the TMA tensor loads (UTMALDG) and mbarrier waits the staged inner iteration uses; the shipped default has none."""
+    import shutil
+    import subprocess
+    from tee_optical_flow_b200.build import build_library
+    tma = build_library(variant="tma")
+    lib = C.CDLL(str(tma))
+    for name in _declared_symbols():
+        assert hasattr(lib, name), f"libteeflow_tma.so does not export {name}"
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not shutil.which(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    count = lambda path, pat: sum(pat in l for l in subprocess.run([cuobjdump, "-sass", str(path)], capture_output=True, text=True).stdout.splitlines())
+    assert count(tma, "UTMALDG.4D") > 0 and count(tma, "SYNCS.PHASECHK") > 0
+    assert count(built_lib, "UTMALDG") == 0
