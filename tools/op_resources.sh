@@ -11,15 +11,19 @@ for spec in "0x02u level_init" "0x04u warp" "0x08u median" "0x10u inner" "0x80u 
   echo "== strip op(s): $2   (-DTEEFLOW_PHASE_MASK=$1)"
   nvcc $FLAGS -DTEEFLOW_PHASE_MASK=$1 -cubin -o /tmp/_op.cubin $SRC 2>&1 | grep -A2 "tvl1_flow_kernelILi1024" | grep -E "spill|Used" | sed 's/^ */   /'
 done
-LIB=tee_optical_flow_b200/libteeflow.so
-echo "== shipped library $LIB: cuobjdump -res-usage (solver kernels)"
+echo "== strip op(s): inner, TMA-staged   (-DTEEFLOW_PHASE_MASK=0x10u -DTEEFLOW_TMA_INNER=1)"
+nvcc $FLAGS -DTEEFLOW_PHASE_MASK=0x10u -DTEEFLOW_TMA_INNER=1 -cubin -o /tmp/_op.cubin $SRC 2>&1 | grep -A2 "tvl1_flow_kernelILi1024" | grep -E "spill|Used" | sed 's/^ */   /'
+for LIB in tee_optical_flow_b200/libteeflow.so tee_optical_flow_b200/libteeflow_tma.so; do
+echo "== library $LIB: cuobjdump -res-usage (solver kernels)"
 cuobjdump -res-usage $LIB 2>/dev/null | grep -A1 -E "tvl1_(flow|step)_kernelILi1024" | grep -v "^--"
-echo "== SASS instruction census of tvl1_flow_kernel<1024> (shipped)"
+echo "== SASS instruction census of tvl1_flow_kernel<1024> ($LIB)"
 cuobjdump -sass $LIB | awk '/Function : .*tvl1_flow_kernelILi1024/{p=1;next} /Function : /{p=0} p' > /tmp/_flow.sass
-for op in "LDG" "STG\|ST\.E" "LDL" "STL" "CCTL.E.PF2" "FFMA2\|FADD2\|FMUL2" "FMNMX" "MUFU" "SHFL" "ATOMG\|ATOM\.\|RED\." "MEMBAR\|ERRBAR" "LDGSTS" "UTMALDG\|UTMASTG\|UBLKCP" "HMMA\|UTC.*MMA" "BAR\.SYNC"; do
+for op in "LDG" "STG\|ST\.E" "LDL" "STL" "CCTL.E.PF2" "FFMA2\|FADD2\|FMUL2" "FMNMX" "MUFU" "SHFL" "ATOMG\|ATOM\.\|RED\." "MEMBAR\|ERRBAR" "LDGSTS" "LDS" "SYNCS" "R2UR" "UTMALDG\|UTMASTG\|UBLKCP" "HMMA\|UTC.*MMA" "BAR\.SYNC"; do
   printf "   %-28s %s\n" "$op" "$(grep -c "$op" /tmp/_flow.sass)"
 done
 echo "   total instructions           $(grep -c '^\s*/\*[0-9a-f]\{4,\}\*/' /tmp/_flow.sass)"
+done
+cuobjdump -sass tee_optical_flow_b200/libteeflow.so | awk '/Function : .*tvl1_flow_kernelILi1024/{p=1;next} /Function : /{p=0} p' > /tmp/_flow.sass
 echo "== where the local-memory accesses (spills) of the shipped kernel sit: offsets of LDL / STL vs the hot loops"
 python3 - <<'PY'
 import re
