@@ -297,6 +297,23 @@ def test_batch_of_clips_equals_per_clip():
             assert np.array_equal(b16[i], c16)
 
 
+def test_batch_cut_into_several_scheduler_runs_changes_nothing():
+    """calc_batch bounds its pyramid workspace by cutting a large batch into scheduler runs (max_frames_per_run): same
+    flows, and last_counters() returns the counters of all runs in batch order"""
+    import torch
+    from tee_optical_flow_b200.synth import make_clip
+    clips = np.stack([make_clip(seed=s, n_frames=5, H=48, W=80, peak_disp=3.0, period=6.0) for s in (40, 41, 42, 43, 44)])
+    d = torch.from_numpy(clips).cuda()
+    with _fresh() as eng:
+        whole32, whole16 = eng.calc_batch(d, want_f32=True, want_f16=True)
+        c_whole, i_whole = eng.last_counters()
+        cut32, cut16 = eng.calc_batch(d, want_f32=True, want_f16=True, max_frames_per_run=10)     # 2 clips per run
+        c_cut, i_cut = eng.last_counters()
+    assert torch.equal(whole32, cut32) and torch.equal(whole16, cut16)
+    assert i_cut["scheduler_runs"] == 3 and i_cut["n_pairs"] == i_whole["n_pairs"] == 20
+    assert np.array_equal(c_whole, c_cut)
+
+
 def test_long_clip_config_1024_7scales_10warps(oracle):
     """BASELINE config 5 geometry: 1024x1024, nscales=7, warps=10 -- one pair against the oracle, bit for bit"""
     from tee_optical_flow_b200.synth import make_clip
