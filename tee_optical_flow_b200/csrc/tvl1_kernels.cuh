@@ -273,6 +273,15 @@ __device__ __forceinline__ int items_of(const EngineParams& P, int phase, int pa
     return phase == PH_INNER ? P.lv[level].in_items : P.lv[level].pw_items;
 }
 
+#ifndef TEEFLOW_CG_NEIGHBOURS
+#define TEEFLOW_CG_NEIGHBOURS 1   // 1: median / level-init read their taps with ld.global.cg too and take no acquire fence
+#endif
+constexpr bool kCgNeighbours = TEEFLOW_CG_NEIGHBOURS != 0;
+__device__ __forceinline__ bool needs_l1_acquire(int phase) {
+    return !kCgNeighbours && (phase == PH_MEDIAN || phase == PH_LEVEL_INIT);
+}
+template <typename T>
+__device__ __forceinline__ T ld_tap(const T* p) { return kCgNeighbours ? __ldcg(p) : *p; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ------------------------------------------------------------------------------------------------ strip ops
@@ -304,8 +313,8 @@ __device__ __forceinline__ void op_level_init(const EngineParams& P, int level, 
         if (!coarsest) {
             int ya, yb; float b0, b1;
             lin_coeff_y(y, g.up_sy, cH, ya, yb, b0, b1);
-            const float2 s00 = SB[L::at(pUs, ya, x0)], s01 = SB[L::at(pUs, ya, x1)];
-            const float2 s10 = SB[L::at(pUs, yb, x0)], s11 = SB[L::at(pUs, yb, x1)];
+            const float2 s00 = ld_tap(SB + L::at(pUs, ya, x0)), s01 = ld_tap(SB + L::at(pUs, ya, x1));
+            const float2 s10 = ld_tap(SB + L::at(pUs, yb, x0)), s11 = ld_tap(SB + L::at(pUs, yb, x1));
             const float r0x = s00.x * a0 + s01.x * a1, r1x = s10.x * a0 + s11.x * a1;
             const float r0y = s00.y * a0 + s01.y * a1, r1y = s10.y * a0 + s11.y * a1;
             u.x = (r0x * b0 + r1x * b1) * P.up_mul;
@@ -389,10 +398,10 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
                 if (interior) {                          // x-2 .. x+2 inside the image: one pointer + immediates
                     const float* q = row + xs[0];
 #pragma unroll
-                    for (int dx = 0; dx < 5; ++dx) v[dx] = q[2 * dx];
+                    for (int dx = 0; dx < 5; ++dx) v[dx] = ld_tap(q + 2 * dx);
                 } else {
 #pragma unroll
-                    for (int dx = 0; dx < 5; ++dx) v[dx] = row[xs[dx]];
+                    for (int dx = 0; dx < 5; ++dx) v[dx] = ld_tap(row + xs[dx]);
                 }
                 TF_MED_SORT5(v)
             };
@@ -431,7 +440,7 @@ __device__ __forceinline__ void op_median(const EngineParams& P, int level, int 
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int xx = clampi(x + dx, 0, g.W - 1);
-                    const float2 t = SB[L::at(pUs, yy, xx)];
+                    const float2 t = ld_tap(SB + L::at(pUs, yy, xx));
                     v[(dy + 1) * 3 + dx + 1] = t.x;
                     w[(dy + 1) * 3 + dx + 1] = t.y;
                 }
@@ -1118,13 +1127,16 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
 // ------------------------------------------------------------------------------------------- strip dispatch
 // How the strip ops read the slot planes (the dataflow kernel re-reads, within ONE launch, planes that other SMs
 // rewrote in the meantime, so the non-coherent ld.global.nc path is never used for them):
-//   * streaming ops (inner, two-iteration pass, warp's flow row, WASE, final): every value is read once, with
-//     ld.global.cg -- served by L2, the point of coherence, so no stale L1 line can be hit;
-//   * ops that re-read neighbours through L1 (median: five taps per row; level-init: the four bilinear taps) use
-//     plain loads, and the warp executes an acquire fence (which also drops the SM's L1 lines) after it was handed
-//     the strip -- needs_l1_acquire().
+//   * every op reads the planes with ld.global.cg -- served by L2, the point of coherence, so no stale L1 line can be
+//     hit and no op depends on a fence dropping L1 lines.  That includes the ops that re-read neighbours (median: five
+//     taps per row; level-init: the four bilinear taps; ld_tap()): their re-reads hit L2 instead of L1, which costs
+//     the ALU-bound median 2 % phase-pure and wins 0.7 % on the clip, because the alternative -- plain loads behind an
+//     acquire fence per strip (TEEFLOW_CG_NEIGHBOURS=0, needs_l1_acquire()) -- throws the SM's whole L1 away every
+//     few microseconds under the warp op's gathers;
+//   * a finished strip arrives at its slot's counter with a release atomic, not __threadfence() + atomicAdd (which is
+//     MEMBAR.SC + CCTL.IVALL: again the whole L1, once per strip; +1.2 % on the clip).
 // Read-only inputs (pyramid, WASE weights) keep ld.global.nc.
-__device__ __forceinline__ bool needs_l1_acquire(int phase) { return phase == PH_MEDIAN || phase == PH_LEVEL_INIT; }
+
 
 #ifndef TEEFLOW_FLOW_STATS
 #define TEEFLOW_FLOW_STATS 0
@@ -1158,6 +1170,24 @@ __device__ __forceinline__ void run_strip(const EngineParams& P, int phase, int 
     else if (has_op(PH_FINAL) && phase == PH_FINAL) op_final<PITCH>(P, ucur, pair, bg, slot, strip, lane);
 }
 
+// Arrival of a finished strip at its slot's counter: a RELEASE atomic (the strip's stores -- all lanes', ordered before
+// lane 0 by the __syncwarp that precedes it -- are visible before the count).  __threadfence() + atomicAdd does the
+// same but compiles to MEMBAR.SC + CCTL.IVALL: every finished strip would throw away the whole L1 of its SM, about
+// once per microsecond, and the warp op's bicubic gathers and the median's row re-reads live there.
+#ifndef TEEFLOW_RELEASE_ARRIVE
+#define TEEFLOW_RELEASE_ARRIVE 1
+#endif
+__device__ __forceinline__ unsigned arrive_release(unsigned* counter) {
+#if TEEFLOW_RELEASE_ARRIVE
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
+#else
+    __threadfence();
+    return atomicAdd(counter, 1u);
+#endif
+}
+
 // lane 0 records the strip's error partial(s) and takes an arrival ticket of the slot; true for the warp that
 // delivered the last strip of the task
 __device__ __forceinline__ bool strip_arrive(const EngineParams& P, int phase, int slot, int strip, int n_items, int lane,
@@ -1169,8 +1199,7 @@ __device__ __forceinline__ bool strip_arrive(const EngineParams& P, int phase, i
             P.partial[(size_t)slot * P.max_tiles + 2 * strip] = err;
             P.partial[(size_t)slot * P.max_tiles + 2 * strip + 1] = aux;
         }
-        __threadfence();
-        const unsigned ticket = atomicAdd(P.arrive + slot, 1u);
+        const unsigned ticket = arrive_release(P.arrive + slot);
         last = (ticket == (unsigned)n_items - 1u);
     }
     return __shfl_sync(0xffffffffu, last, 0) != 0;
@@ -1503,8 +1532,7 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
 #else
             t = atomicAdd(&F->ticket, 1u);             // travels while the fence below drains this strip's stores
 #endif
-            __threadfence();
-            pend_arrive = atomicAdd(P.arrive + slot, 1u);
+            pend_arrive = arrive_release(P.arrive + slot);
         }
         pend_n = n_items; pend_slot = slot; pend_phase = phase;
     }
