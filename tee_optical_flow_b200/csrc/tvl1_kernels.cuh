@@ -45,6 +45,10 @@ constexpr int kInnerUnroll = TEEFLOW_INNER_UNROLL;   // rows per trip of the sin
 #define TEEFLOW_WARP_PF 0
 #endif
 constexpr int kWarpPF = TEEFLOW_WARP_PF;   // warp op: tap rows pulled into L2 ahead of the gather window (0: off)
+#ifndef TEEFLOW_WARP_PF1
+#define TEEFLOW_WARP_PF1 2
+#endif
+constexpr int kWarpPF1 = TEEFLOW_WARP_PF1; // warp op: tap rows that enter the window kWarpPF1 pixel rows from now are pulled into L1 (0: off)
 #ifndef TEEFLOW_LATE_HANDOVER
 #define TEEFLOW_LATE_HANDOVER 1
 #endif
@@ -283,6 +287,7 @@ __device__ __forceinline__ bool needs_l1_acquire(int phase) {
 template <typename T>
 __device__ __forceinline__ T ld_tap(const T* p) { return kCgNeighbours ? __ldcg(p) : *p; }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ------------------------------------------------------------------------------------------------ strip ops
 // Slot planes live in the row-interleaved constant-pitch layout of struct Lay (tvl1_device.cuh).
@@ -356,6 +361,12 @@ __device__ __forceinline__ void op_warp(const EngineParams& P, int level, int uc
             // row that enters it kWarpPF rows from now is pulled into L2 already (4 taps x 16 bytes per lane)
             const int pr = min(max((int)my + 2 + kWarpPF, 0), g.H - 1), pcx = min(max((int)mx - 1, 0), g.W - 1);
             prefetch_l2(G1 + (unsigned)(pr * g.W + pcx));
+        }
+        if (kWarpPF1 > 0) {
+            // consecutive pixel rows share three of their four tap rows; the one that enters (four taps = 64 bytes per
+            // lane) is requested ahead, so that its gather finds it in L1 instead of waiting for L2
+            const int pr = min(max((int)my + 2 + kWarpPF1, 0), g.H - 1), pcx = min(max((int)mx - 1, 0), max(g.W - 4, 0));
+            prefetch_l1(G1 + (unsigned)(pr * g.W + pcx));
         }
         const float3 w = remap_cubic3(G1, g.H, g.W, mx, my, s_cubic, P.negzero);
         const float Ix2 = w.y * w.y, Iy2 = w.z * w.z;

@@ -1,5 +1,3 @@
-bash tools/variant_ab.sh " " "-DTEEFLOW_CG_NEIGHBOURS=1" " " > gpurun_out/r2v_ab.log 2>&1; cat gpurun_out/r2v_ab.log
-TEEFLOW_NVCC_EXTRA="-DTEEFLOW_CG_NEIGHBOURS=1" python -m tee_optical_flow_b200.build --force > /dev/null 2>&1
+bash tools/variant_ab.sh " " "-DTEEFLOW_POINT_ROWS=32" "-DTEEFLOW_WARP_PF=5" "-DTEEFLOW_POINT_ROWS=24" " " > gpurun_out/r2x_ab.log 2>&1; cat gpurun_out/r2x_ab.log
 python tools/phase_times.py 2>&1 | grep '"ms"' | head -4
 timeout 600 python -m pytest tests/test_engine_gpu.py -m gpu -x -q 2>&1 | tail -2
-python -m tee_optical_flow_b200.build --force > /dev/null 2>&1
