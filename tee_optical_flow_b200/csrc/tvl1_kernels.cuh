@@ -1152,9 +1152,6 @@ __device__ __forceinline__ void op_final(const EngineParams& P, int ucur, int pa
 #ifndef TEEFLOW_FLOW_STATS
 #define TEEFLOW_FLOW_STATS 0
 #endif
-#ifndef TEEFLOW_EARLY_TICKET
-#define TEEFLOW_EARLY_TICKET 0   // dataflow scheduler: request the next strip ticket when a strip starts (not when it ends)
-#endif
 #ifndef TEEFLOW_EARLY_PROBE
 #define TEEFLOW_EARLY_PROBE 1    // dataflow scheduler: read the task descriptors at the cursor before the release fence
 #endif
@@ -1443,9 +1440,6 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
     if (lane == 0) t = atomicAdd(&F->ticket, 1u);
     unsigned pend_arrive = 0, pend_n = 0;              // pend_n == 0: nothing pending
     int pend_slot = 0, pend_phase = 0;
-#if TEEFLOW_EARLY_TICKET
-    unsigned t_next = 0;                               // lane 0: the ticket after t, requested when strip t starts
-#endif
 #if TEEFLOW_EARLY_PROBE
     uint4 d_early = make_uint4(0u, 0u, 0u, 0u);        // descriptors at the cursor, read before the release fence
     bool have_early = false;
@@ -1516,11 +1510,6 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
         const int strip = (int)(t - desc.y);
         if (needs_l1_acquire(phase)) __threadfence();  // plain (L1) plane reads ahead: drop the SM's stale lines
         const float bg = (phase == PH_FINAL && P.wase_w) ? __ldcg(P.bg_out + pair) : 0.f;
-#if TEEFLOW_EARLY_TICKET
-        // the next ticket travels while this strip runs.  (Still deadlock free: a warp that WAITS for a task holds no
-        // other ticket, and a ticket held in advance sits behind a strip that runs to its end without waiting.)
-        if (lane == 0) t_next = atomicAdd(&F->ticket, 1u);
-#endif
         TF_STAT(10)
 
         double err = 0.0, aux = 0.0;
@@ -1538,11 +1527,9 @@ tvl1_flow_kernel(const __grid_constant__ EngineParams P) {
                 P.partial[(size_t)slot * P.max_tiles + 2 * strip] = err;
                 P.partial[(size_t)slot * P.max_tiles + 2 * strip + 1] = aux;
             }
-#if TEEFLOW_EARLY_TICKET
-            t = t_next;
-#else
-            t = atomicAdd(&F->ticket, 1u);             // travels while the fence below drains this strip's stores
-#endif
+            // travels while the release below drains this strip's stores.  (Requesting it already when the strip STARTS
+            // was measured: 9 % slower -- a strip that is claimed but not started delays the completion of its task.)
+            t = atomicAdd(&F->ticket, 1u);
             pend_arrive = arrive_release(P.arrive + slot);
         }
         pend_n = n_items; pend_slot = slot; pend_phase = phase;
