@@ -5,6 +5,7 @@ import os
 import sys
 from pathlib import Path
 os.environ.setdefault("TEEFLOW_GROUPS", "1")
+os.environ.setdefault("TEEFLOW_STEPPED", "1")   # one launch per phase step (the default scheduler is one launch per run)
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import torch
 from tee_optical_flow_b200.engine import TVL1Engine
